@@ -1,0 +1,52 @@
+"""How each interpolant fixture in tests/golden/ was set up (mirrors make_golden.py) but
+expressed with THIS repo's host API, so the same case can be rebuilt by the oracle and by
+the CUDA path on the GPU box (where /root/reference does not exist)."""
+import numpy as np
+
+# name -> (knot family, lev2knots name, operator kind)
+CASES = {
+    "lin_deg1": ("equi", "n+1", "linear"),
+    "cub_deg3": ("equi", "3n+1", "cubic"),
+    "lin_exp_cc": ("cc", "n+1", "linear"),
+    "lin_gauss_rf": ("optg", "2^(n+1)-1", "linear"),
+    "lin_cc_nested": ("cc", "doubling", "linear"),
+    "quad_cc_nested": ("cc", "doubling", "quadratic"),
+    "quad_aniso5": ("equi_arr", "doubling", "quadratic"),
+    "cub_smolyak3": ("equi_arr", "3n+1", "cubic"),
+    "lag_example0": ("cc", "example0", "lagrange"),
+    "lin_example0": ("cc", "example0", "linear"),
+    "lag_hermite": ("hermite", "n+1", "lagrange"),
+    "lin_example1": ("unb", "2^(n+1)-1", "linear"),
+    "lin_c2_small": ("unb", "2^(n+1)-1", "linear"),
+}
+
+LEV2KNOTS = {
+    "n+1": lambda n: n + 1,
+    "3n+1": lambda n: 3 * n + 1,
+    "2^(n+1)-1": lambda n: 2 ** (n + 1) - 1,
+    "doubling": lambda n: np.where(n == 0, 1, 2 ** n + 1),
+    "example0": lambda n: np.where(0, 1, 2 ** n + 1),
+}
+
+
+def knot_family(name, nodes_module):
+    n1d = nodes_module
+    return {
+        "equi": n1d.equispaced_nodes,
+        "equi_arr": lambda n: np.atleast_1d(np.asarray(n1d.equispaced_nodes(n), dtype=float)),
+        "cc": n1d.cc_nodes,
+        "optg": lambda n: n1d.optimal_gaussian_nodes(n, p=2),
+        "unb": n1d.unbounded_nodes_nested,
+        "hermite": n1d.hermite_nodes,
+    }[name]
+
+
+def unpack_plan(g):
+    """Lists (dims, shapes, maps) from the packed arrays written by make_golden.pack_plan."""
+    T = g["coeffs"].shape[0]
+    dims = [g["dims"][g["dims_off"][t]:g["dims_off"][t + 1]] for t in range(T)]
+    shapes = [tuple(int(v) for v in g["shapes"][g["shape_off"][t]:g["shape_off"][t + 1]])
+              for t in range(T)]
+    maps = [g["maps"][g["map_off"][t]:g["map_off"][t + 1]].reshape(shapes[t])
+            for t in range(T)]
+    return dims, shapes, maps
