@@ -1,0 +1,176 @@
+/*
+ * sgm_b200.h -- C ABI of libsgm_b200.so, the B200 (sm_100a) evaluation engine for
+ * combination-technique sparse-grid interpolants.
+ *
+ * This is the drop-in boundary for ONE hot path of andreascaglioni/SGMethods:
+ *     SGInterpolant.__init__ tables  ->  SGInterpolant.interpolate(x_new, f_on_SG)
+ * (reference: sgmethods/sparse_grid_interpolant.py:65-139 and :252-279) together with the
+ * tensor-product operators it calls per combination term
+ * (sgmethods/tp_interpolant_wrapper.py:41-64, sgmethods/tp_inteprolants.py:38-53, :83-160,
+ * :189-277, :322-360) and the Levy-Ciesielski expansion
+ * (sgmethods/parametric_expansions_brownian_motion.py:17-71).
+ *
+ * Conventions
+ *   - plain C types only; no torch / numpy types cross this boundary;
+ *   - every function returns 0 on success or a negative sgm_status; the message of the
+ *     last failure on the calling thread is available from sgm_last_error();
+ *   - "host" functions touch no GPU state and work on machines without a GPU;
+ *   - device pointers are fp64, row-major, with explicit leading dimensions; buffers are
+ *     owned by the caller, the library allocates nothing on the device except the
+ *     immutable plan tables;
+ *   - kernels are enqueued on the given stream and are asynchronous w.r.t. the host; a plan
+ *     is read-only after creation and may be used from several threads / streams.
+ */
+#ifndef SGM_B200_H
+#define SGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sgm_status {
+    SGM_OK = 0,
+    SGM_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsorted set, ...)      */
+    SGM_ERR_CUDA = -2,        /* a CUDA runtime call failed                                 */
+    SGM_ERR_OVERFLOW = -3,    /* a table does not fit the packed 32-bit layout              */
+    SGM_ERR_NODE_TOL = -4,    /* 1-D knots not separable at the reference's 1e-10 tolerance */
+    SGM_ERR_WORKSPACE = -5    /* caller-provided workspace too small                        */
+} sgm_status;
+
+/* Operator kinds = the reference's four tensor-product operator classes. */
+typedef enum sgm_kind {
+    SGM_PW_LINEAR = 0,        /* TPPwLinearInterpolator    tp_inteprolants.py:21-53   */
+    SGM_PW_QUADRATIC = 1,     /* TPPwQuadraticInterpolator tp_inteprolants.py:55-160  */
+    SGM_PW_CUBIC = 2,         /* TPPwCubicInterpolator     tp_inteprolants.py:162-277 */
+    SGM_LAGRANGE = 3          /* TPLagrangeInterpolator    tp_inteprolants.py:279-360 */
+} sgm_kind;
+
+/* Bits reported by sgm_plan_take_flags(): conditions on which the reference raises. */
+#define SGM_FLAG_QUADRATIC_RIGHT 1u  /* pw-quadratic point right of the last knot or NaN:
+                                        IndexError in the reference (tp_inteprolants.py:131) */
+
+const char* sgm_last_error(void);
+int sgm_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host table construction (integer work, bit-exact with the reference)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Combination-technique coefficients  c_nu = sum_{e in {0,1}^N, nu+e in set} (-1)^{|e|}
+ * for every row of a lexicographically sorted, downward-closed multi-index set.
+ * Replaces the window search of SGInterpolant.setup_interpolant
+ * (sparse_grid_interpolant.py:77-92).  mid_set: card x N, row-major.  coeffs: card. */
+int sgm_host_combination_coeffs(const int64_t* mid_set, int64_t card, int32_t N,
+                                int64_t* coeffs);
+
+/* Sparse-grid node numbering.  Replaces SGInterpolant.setup_SG
+ * (sparse_grid_interpolant.py:109-139): terms are walked in order, the nodes of a term in C
+ * order over its active directions (num_nodes > 1, ascending), each node is embedded in R^N
+ * with 0 in the inactive directions, nodes closer than `tol` in the 1-norm are merged, rows
+ * are numbered by first appearance and keep the coordinates of their first appearance.
+ * O(total nodes) via hashing instead of the reference's O(M^2) search.
+ *   num_nodes  T x N   nodes per direction of every active term (lev2knots(nu).astype(int))
+ *   fam_m      n_fam   the distinct values > 1 in num_nodes (plus 1 if present is ignored)
+ *   fam_off    n_fam+1 offsets into fam_knots
+ *   fam_knots          knots(m) for each family member, ascending order not required here  */
+typedef struct sgm_grid sgm_grid;
+int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam,
+                   const int32_t* fam_m, const int64_t* fam_off, const double* fam_knots,
+                   double tol, sgm_grid** out);
+int64_t sgm_grid_num_nodes(const sgm_grid* g);     /* M                                   */
+int64_t sgm_grid_map_size(const sgm_grid* g);      /* sum_t S_t                           */
+int64_t sgm_grid_nnz(const sgm_grid* g);           /* non-zero coordinates over all nodes */
+/* map_off: T+1 offsets; maps: concatenated C-order maps term -> row of SG (int32). */
+int sgm_grid_copy_maps(const sgm_grid* g, int64_t* map_off, int32_t* maps);
+/* dense M x N coordinate matrix (the reference's SG attribute), float-bit-exact. */
+int sgm_grid_copy_nodes_dense(const sgm_grid* g, double* SG);
+/* CSR form of the same matrix: row_off M+1, cols/vals nnz (entries stored even when the
+ * first-seen coordinate is a signed zero are NOT listed; they read back as +0.0). */
+int sgm_grid_copy_nodes_csr(const sgm_grid* g, int64_t* row_off, int32_t* cols, double* vals);
+void sgm_grid_destroy(sgm_grid* g);
+
+/* Row matching used by sample_on_SG's recycling (sparse_grid_interpolant.py:214-231): for
+ * every row of `xx` (n x N) the index of the unique row of `old_xx` (n_old x N) with
+ * 1-norm distance < tol, or -1.  Returns SGM_ERR_INVALID if a row has several matches
+ * (the reference asserts).  Hash-accelerated, exact same acceptance test. */
+int sgm_host_match_rows(const double* xx, int64_t n, const double* old_xx, int64_t n_old,
+                        int32_t N, double tol, int64_t* match);
+
+/* ------------------------------------------------------------------------------------------
+ * Device plan = packed tables of one interpolant (immutable after creation)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sgm_plan_desc {
+    int32_t kind;              /* sgm_kind                                                  */
+    int32_t N;                 /* parametric dimension                                      */
+    int64_t T;                 /* active terms (c != 0), reference order                    */
+    int64_t M;                 /* rows of f_on_SG this plan addresses                       */
+    const double* coeffs;      /* T    combination coefficients (exact integers in fp64)    */
+    const int32_t* term_fam;   /* T*N  knot family of each direction, -1 = inactive (1 node) */
+    const int64_t* map_off;    /* T+1                                                       */
+    const int32_t* maps;       /* map_off[T] rows of f_on_SG, C order per term              */
+    int32_t n_fam;             /* knot families (SGInterpolant: one per distinct node count) */
+    const int64_t* fam_off;    /* n_fam+1 offsets into fam_knots / fam_lambda               */
+    const double* fam_knots;   /* knots of each family, ascending, >= 2 per family          */
+    const double* fam_lambda;  /* barycentric lambda per knot (SGM_LAGRANGE only, else NULL) */
+} sgm_plan_desc;
+
+typedef struct sgm_plan sgm_plan;
+int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out);
+void sgm_plan_destroy(sgm_plan* plan);
+/* Bytes of packed tables resident on the device / walked once per launch. */
+int64_t sgm_plan_table_bytes(const sgm_plan* plan);
+/* sum_t C_t = corner (or node) contributions per point and output: 2^k, 3^k, 4^k or S_t. */
+int64_t sgm_plan_corners_per_point(const sgm_plan* plan);
+/* Reads and clears the condition flags set by kernels launched with this plan
+ * (synchronises `stream`). */
+int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags);
+
+/* Scratch the caller must provide to sgm_eval for P points and NF outputs (device bytes). */
+size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF);
+
+/* out[p, 0:NF] = sum_t c_t * TP_t(x[p, active dims of t])   -- replaces the Python term loop
+ * of SGInterpolant.interpolate (sparse_grid_interpolant.py:268-279), the wrapper's column
+ * purge / constant path (tp_interpolant_wrapper.py:54-64) and the four operator classes.
+ *   x    P x ldx (ldx >= N; only the first N columns are read)           device, fp64
+ *   f    M x ldf (ldf >= NF) values on the sparse grid, row-major         device, fp64
+ *   out  P x ldo (ldo >= NF)                                              device, fp64
+ * Arithmetic order per (point, output) follows the reference exactly.  */
+int sgm_eval(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
+             const double* f, int64_t M, int64_t NF, int64_t ldf,
+             double* out, int64_t ldo, void* workspace, size_t workspace_bytes,
+             void* stream);
+
+/* Multilevel combination (reference: MLInterpolant.interpolate / get_ml_terms,
+ * sgmethods/multilevel_interpolant.py:89-150): for n_parts plans sharing the points x,
+ *   out = sum_i sign_i * I_{plan_i}[f_i](x)
+ * evaluated part after part on one stream with a fused signed accumulation into `out`
+ * (first part overwrites).  f[i] is M_i x ldf[i]. */
+int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_parts,
+                        const double* x, int64_t P, int64_t ldx,
+                        const double* const* f, const int64_t* M, const int64_t* ldf,
+                        int64_t NF, double* out, int64_t ldo,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* W[p, :] = Levy-Ciesielski expansion of Brownian motion on [0, T] at times tt for the
+ * parameter vector yy[p, 0:d]  (reference: param_LC_Brownian_motion,
+ * sgmethods/parametric_expansions_brownian_motion.py:17-71, one call per row there).
+ *   tt nt, yy P x ldy (ldy >= d), W P x ldw (ldw >= nt), level_scale[l-1] = 2^((l-1)/2) for
+ *   l = 1..L with L = ceil(log2 d) and sqrtT = sqrt(T) (host-computed so that the factors
+ *   are bit-identical to the reference's python/numpy values). */
+int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, int32_t d,
+                    int64_t ldy, double T, double sqrtT, const double* level_scale, int32_t L,
+                    double* W, int64_t ldw, void* stream);
+
+/* W[p, :] = sum_n factor[n] * sin(freq[n] * tt) * yy[p, n]  (param_KL_Brownian_motion as
+ * shipped, parametric_expansions_brownian_motion.py:73-91; factor/freq host-computed). */
+int sgm_kl_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, int32_t d,
+                    int64_t ldy, const double* factor, const double* freq,
+                    double* W, int64_t ldw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGM_B200_H */

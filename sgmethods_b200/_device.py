@@ -1,0 +1,133 @@
+"""Device-side plumbing: torch is used for device memory, streams and device selection only;
+all arithmetic runs in the kernels of libsgm_b200.so.  There is no CPU fallback: every
+function here raises if CUDA is unavailable."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def torch_cuda():
+    """torch, after checking that a CUDA device is usable."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("sgmethods_b200 evaluates on a CUDA device (B200, sm_100a) and has "
+                           "no CPU fallback: torch.cuda.is_available() is False")
+    return torch
+
+
+def lagrange_lambdas(g):
+    """lambda_i = 1 / prod_{j != i, ascending} (g_i - g_j) with the reference's operation
+    order (tp_inteprolants.py:311-320); host side because it is part of operator set-up."""
+    g = np.asarray(g, dtype=np.float64)
+    lam = np.ones(g.shape[0])
+    for i in range(g.shape[0]):
+        keep = np.ones(g.shape[0], dtype=bool)
+        keep[i] = False
+        lam[i] = np.prod(g[i] - g, where=keep)
+    return 1 / lam
+
+
+class DevicePlan:
+    """Packed tables of one interpolant resident on one GPU (sgm_plan)."""
+
+    def __init__(self, kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
+                 device=None):
+        """term_fam: (T, N) knot-family index per direction, -1 where the term has one node;
+        fam_off / fam_knots: CSR list of the families' ascending knot vectors."""
+        torch = torch_cuda()
+        lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.kind, self.N, self.M = int(kind), int(N), int(M)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        term_fam = np.ascontiguousarray(term_fam, dtype=np.int32).reshape(-1, self.N)
+        map_off = np.ascontiguousarray(map_off, dtype=np.int64)
+        maps = np.ascontiguousarray(maps, dtype=np.int32)
+        fam_off = np.ascontiguousarray(fam_off, dtype=np.int64)
+        n_fam = fam_off.size - 1
+        fam_knots = np.ascontiguousarray(fam_knots, dtype=np.float64)
+        lam = None
+        if kind == _lib.KIND_LAGRANGE:
+            lam = np.concatenate([lagrange_lambdas(fam_knots[fam_off[i]:fam_off[i + 1]])
+                                  for i in range(n_fam)]) if n_fam else np.zeros(0)
+        self.T = coeffs.shape[0]
+        desc = _lib.PlanDesc(
+            kind=self.kind, N=self.N, T=self.T, M=self.M,
+            coeffs=_lib.ptr(coeffs, _lib.c_f64), term_fam=_lib.ptr(term_fam, _lib.c_i32),
+            map_off=_lib.ptr(map_off, _lib.c_i64), maps=_lib.ptr(maps, _lib.c_i32),
+            n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
+            fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
+            fam_lambda=_lib.ptr(lam, _lib.c_f64))
+        handle = _lib.c_vp()
+        _lib.check(lib.sgm_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
+        self._h = handle
+        self.table_bytes = int(lib.sgm_plan_table_bytes(handle))
+        self.corners_per_point = int(lib.sgm_plan_corners_per_point(handle))
+        self._workspace = None
+
+    # -- evaluation -------------------------------------------------------------------------
+    def workspace(self, P, NF):
+        torch = torch_cuda()
+        need = int(_lib.load().sgm_eval_workspace_bytes(self._h, P, NF))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8,
+                                          device=torch.device("cuda", self.device))
+        return self._workspace
+
+    def eval(self, x, f, out=None):
+        """x (P, >=N), f (M, NF), both fp64 CUDA tensors on this plan's device -> (P, NF)."""
+        torch = torch_cuda()
+        assert x.is_cuda and f.is_cuda and x.dtype == torch.float64 and f.dtype == torch.float64
+        assert x.dim() == 2 and f.dim() == 2 and x.stride(1) == 1 and f.stride(1) == 1
+        P, NF = x.shape[0], f.shape[1]
+        if out is None:
+            out = torch.empty((P, NF), dtype=torch.float64, device=x.device)
+        ws = self.workspace(P, NF)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().sgm_eval(
+            self._h, x.data_ptr(), P, x.stride(0) if P > 1 else max(x.shape[1], 1),
+            f.data_ptr(), f.shape[0], NF, f.stride(0) if f.shape[0] > 1 else max(NF, 1),
+            out.data_ptr(), out.stride(0) if P > 1 else max(NF, 1), ws.data_ptr(), ws.numel(),
+            stream))
+        return out
+
+    def take_flags(self):
+        torch = torch_cuda()
+        flags = ctypes.c_uint32(0)
+        stream = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        _lib.check(_lib.load().sgm_plan_take_flags(self._h, stream, ctypes.byref(flags)))
+        return flags.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().sgm_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def signed_sum(plans, signs, x, fs, out=None):
+    """out = sum_i signs[i] * plans[i](x; fs[i]) in one ABI call (sgm_eval_signed_sum)."""
+    torch = torch_cuda()
+    n = len(plans)
+    P, NF = x.shape[0], fs[0].shape[1]
+    if out is None:
+        out = torch.empty((P, NF), dtype=torch.float64, device=x.device)
+    need = max(int(_lib.load().sgm_eval_workspace_bytes(p._h, P, NF)) for p in plans)
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    handles = (_lib.c_vp * n)(*[p._h for p in plans])
+    fptr = (_lib.c_vp * n)(*[f.data_ptr() for f in fs])
+    Ms = (_lib.c_i64 * n)(*[f.shape[0] for f in fs])
+    ldf = (_lib.c_i64 * n)(*[f.stride(0) if f.shape[0] > 1 else max(NF, 1) for f in fs])
+    sg = (_lib.c_f64 * n)(*[float(s) for s in signs])
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.load().sgm_eval_signed_sum(
+        handles, sg, n, x.data_ptr(), P, x.stride(0) if P > 1 else max(x.shape[1], 1), fptr, Ms,
+        ldf, NF, out.data_ptr(), out.stride(0) if P > 1 else max(NF, 1), ws.data_ptr(),
+        ws.numel(), stream))
+    return out

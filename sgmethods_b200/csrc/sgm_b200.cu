@@ -1,0 +1,424 @@
+// sgm_b200.cu -- C ABI of libsgm_b200.so (see include/sgm_b200.h): plan packing / upload,
+// launch heuristics and the entry points that enqueue the kernels of sgm_kernels.cuh.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sgm_internal.h"
+#include "sgm_kernels.cuh"
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+int sgm_fail(int code, const char* msg) {
+    g_last_error = msg ? msg : "";
+    return code;
+}
+int sgm_failf(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SGM_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t err__ = (call);                                                        \
+        if (err__ != cudaSuccess)                                                          \
+            return sgm_failf(SGM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__)); \
+    } while (0)
+
+using sgm::Entry;
+using sgm::PlanDev;
+using sgm::TermDim;
+using sgm::TermHdr;
+
+struct sgm_plan {
+    int device = 0;
+    PlanDev dev{};
+    int64_t n_vals = 0;          // sum_t S_t
+    int64_t corners = 0;         // sum_t C_t
+    int64_t table_bytes = 0;
+    int kmax = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    std::vector<void*> allocations;
+};
+
+namespace {
+
+template <class T>
+int upload(sgm_plan* plan, const std::vector<T>& host, const T** dev_ptr) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+    SGM_CUDA(cudaMalloc(&d, bytes));
+    plan->allocations.push_back(d);
+    if (!host.empty())
+        SGM_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    plan->table_bytes += (int64_t)(host.size() * sizeof(T));
+    *dev_ptr = static_cast<const T*>(d);
+    return SGM_OK;
+}
+
+int radix_of(int kind, int m) {
+    switch (kind) {
+        case SGM_PW_LINEAR: return 2;
+        case SGM_PW_QUADRATIC: return 3;
+        case SGM_PW_CUBIC: return 4;
+        default: return m;
+    }
+}
+int basis_width(int kind, int m) {
+    switch (kind) {
+        case SGM_PW_LINEAR: return 1;       // y; the lower weight 1 - y is formed on use
+        case SGM_PW_QUADRATIC: return 3;
+        case SGM_PW_CUBIC: return 4;
+        default: return m;
+    }
+}
+
+// Launch shape of kernel A (one thread per point).
+struct PointLaunch { int threads; size_t smem; bool global_basis; int blocks_per_sm; };
+
+PointLaunch choose_point_launch(const sgm_plan* plan) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (d.kind == SGM_LAGRANGE ? 2 : 1);
+    const size_t per_point = (size_t)d.B * 8 + (size_t)d.E * 2;
+    const size_t cap = (size_t)plan->max_smem_optin;
+    const size_t per_sm = 228 * 1024;
+    PointLaunch best{0, 0, true, 0};
+    size_t best_threads = 0;
+    for (int threads : {128, 64, 32}) {
+        const size_t smem = fixed + per_point * threads;
+        if (smem > cap) continue;
+        const int bps = (int)std::min<size_t>(16, per_sm / (smem + 1024));
+        if (bps < 1) continue;
+        const size_t resident = (size_t)bps * threads;
+        if (resident > best_threads) {
+            best_threads = resident;
+            best = PointLaunch{threads, smem, false, bps};
+        }
+    }
+    if (best.threads == 0 || best_threads < 128) {
+        // basis tables do not fit next to enough threads: keep them in a global scratch
+        if (fixed <= cap) return PointLaunch{128, fixed, true, 4};
+    }
+    return best;
+}
+
+template <int KIND>
+int launch_points(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
+                  double* out, int64_t ldo, double scale, int accumulate, unsigned char* scratch,
+                  size_t scratch_bytes, cudaStream_t stream) {
+    const PointLaunch L = choose_point_launch(plan);
+    if (L.threads == 0) return sgm_fail(SGM_ERR_OVERFLOW, "knot tables exceed shared memory");
+    const int64_t tiles = (P + L.threads - 1) / L.threads;
+    int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm * 8);
+    if (L.global_basis) {
+        blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+        const size_t need = (size_t)blocks * L.threads * ((size_t)plan->dev.B * 8 + (size_t)plan->dev.E * 2);
+        if (need > scratch_bytes) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for basis scratch");
+        auto kern = sgm::eval_points_kernel<KIND, true>;
+        SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+        kern<<<(unsigned)blocks, L.threads, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+                                                              scale, accumulate, scratch);
+    } else {
+        auto kern = sgm::eval_points_kernel<KIND, false>;
+        SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+        kern<<<(unsigned)blocks, L.threads, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+                                                              scale, accumulate, nullptr);
+    }
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+template <int KIND, int CPL>
+int launch_cols_cpl(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                    int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
+                    int accumulate, cudaStream_t stream) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1);
+    const size_t per_warp = (size_t)d.B * 8 + (size_t)d.E * 4;
+    int warps = 8;
+    while (warps > 1 && fixed + per_warp * warps > (size_t)plan->max_smem_optin) warps >>= 1;
+    const size_t smem = fixed + per_warp * warps;
+    if (smem > (size_t)plan->max_smem_optin)
+        return sgm_fail(SGM_ERR_OVERFLOW, "per-point basis table exceeds shared memory");
+    const int pts_per_block = warps * 8;
+    const int64_t gx = (P + pts_per_block - 1) / pts_per_block;
+    const int64_t gy = (NF + 32 * CPL - 1) / (32 * CPL);
+    if (gx > 0x7fffffff || gy > 65535) return sgm_fail(SGM_ERR_OVERFLOW, "grid too large");
+    auto kern = sgm::eval_cols_kernel<KIND, CPL>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)gy), warps * 32, smem, stream>>>(
+        plan->dev, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, pts_per_block);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+template <int KIND>
+int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale, int accumulate,
+                cudaStream_t stream) {
+    if (NF <= 32) return launch_cols_cpl<KIND, 1>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+    if (NF <= 64) return launch_cols_cpl<KIND, 2>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+    return launch_cols_cpl<KIND, 4>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t M,
+             int64_t NF, int64_t ldf, double* out, int64_t ldo, double scale, int accumulate,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!plan) return sgm_fail(SGM_ERR_INVALID, "eval: null plan");
+    if (P < 0 || NF < 1 || ldx < plan->dev.N || ldf < NF || ldo < NF)
+        return sgm_fail(SGM_ERR_INVALID, "eval: bad shapes / leading dimensions");
+    if (M != 0 && M < 0) return sgm_fail(SGM_ERR_INVALID, "eval: bad M");
+    if (P == 0) return SGM_OK;
+    if (!x || !f || !out) return sgm_fail(SGM_ERR_INVALID, "eval: null buffer");
+    SGM_CUDA(cudaSetDevice(plan->device));
+    const int kind = plan->dev.kind;
+    if (NF == 1) {
+        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        if (workspace_bytes < g_bytes || !workspace)
+            return sgm_fail(SGM_ERR_WORKSPACE, "eval: workspace too small");
+        double* G = static_cast<double*>(workspace);
+        unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
+        const int64_t n = plan->n_vals;
+        const int gblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plan->sm_count * 8);
+        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(plan->dev.maps, n, f, ldf, 1, G);
+        SGM_CUDA(cudaGetLastError());
+        const size_t sb = workspace_bytes - g_bytes;
+        switch (kind) {
+            case SGM_PW_LINEAR: return launch_points<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_QUADRATIC: return launch_points<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_CUBIC: return launch_points<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            default: return launch_points<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+        }
+    }
+    switch (kind) {
+        case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+        case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+        case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+        default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sgm_last_error(void) { return g_last_error.c_str(); }
+int sgm_version(void) { return 100; }
+
+int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
+    if (!out) return sgm_fail(SGM_ERR_INVALID, "plan_create: null output");
+    *out = nullptr;
+    if (!desc || desc->N <= 0 || desc->T < 0 || desc->kind < 0 || desc->kind > 3)
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: bad descriptor");
+    if (desc->T > 0 && (!desc->coeffs || !desc->term_fam || !desc->map_off || !desc->maps))
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: null table");
+    if (desc->T > 0x7fffffff) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: too many terms");
+    const int kind = desc->kind;
+    const int N = desc->N;
+    const int64_t T = desc->T;
+    if (desc->n_fam < 0 || (desc->n_fam > 0 && (!desc->fam_off || !desc->fam_knots)))
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: bad family table");
+    if (kind == SGM_LAGRANGE && desc->n_fam > 0 && !desc->fam_lambda)
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: Lagrange plan without lambda table");
+    for (int f = 0; f < desc->n_fam; ++f) {
+        const int64_t m = desc->fam_off[f + 1] - desc->fam_off[f];
+        if (m < 2) return sgm_fail(SGM_ERR_INVALID, "plan_create: knot family with fewer than 2 knots");
+        if (m > 65535) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: more than 65535 knots in one direction");
+    }
+    const int64_t n_knots = desc->n_fam ? desc->fam_off[desc->n_fam] : 0;
+    if (n_knots > 0x3fffffff) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: knot table too large");
+
+    // entries = distinct (direction, family) pairs in order of first use
+    std::vector<int> entry_of((size_t)N * std::max(desc->n_fam, 1), -1);
+    std::vector<Entry> entries;
+    std::vector<TermHdr> hdr((size_t)T);
+    std::vector<TermDim> tdim;
+    int B = 0;
+    int64_t corners = 0;
+    int kmax = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        const int32_t* fam_row = desc->term_fam + t * N;
+        const int64_t off = desc->map_off[t];
+        const int64_t S = desc->map_off[t + 1] - off;
+        if (off > 0x7fffffff || S > 0x7fffffff)
+            return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: node maps exceed the 32-bit packed layout");
+        TermHdr h{0, (int)tdim.size(), (int)off, 1};
+        int64_t check = 1, ncorner = 1;
+        for (int n = 0; n < N; ++n) {
+            const int fam = fam_row[n];
+            if (fam < 0) continue;
+            if (fam >= desc->n_fam)
+                return sgm_fail(SGM_ERR_INVALID, "plan_create: family index out of range");
+            const int m = (int)(desc->fam_off[fam + 1] - desc->fam_off[fam]);
+            int& e = entry_of[(size_t)n * desc->n_fam + fam];
+            if (e < 0) {
+                e = (int)entries.size();
+                entries.push_back(Entry{n, (int)desc->fam_off[fam], m, B});
+                B += basis_width(kind, m);
+            }
+            tdim.push_back(TermDim{entries[e].boff, 0, radix_of(kind, m), e});
+            check *= m;
+            ncorner *= radix_of(kind, m);
+            if (ncorner > 0x3fffffff || check > 0x7fffffff)
+                return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: term with more than 2^30 corner contributions");
+            ++h.k;
+        }
+        if (check != S) return sgm_fail(SGM_ERR_INVALID, "plan_create: map size does not match node counts");
+        int stride = 1;                                    // C order: last active direction fastest
+        for (int j = h.k - 1; j >= 0; --j) {
+            TermDim& d = tdim[h.dim_off + j];
+            d.stride = stride;
+            stride *= entries[d.ent].n;
+        }
+        h.ncorner = (int)ncorner;
+        hdr[t] = h;
+        corners += ncorner;
+        kmax = std::max(kmax, h.k);
+    }
+    for (int64_t i = 0; i < desc->map_off[T]; ++i)
+        if (desc->maps[i] < 0 || desc->maps[i] >= desc->M)
+            return sgm_fail(SGM_ERR_INVALID, "plan_create: map entry outside [0, M)");
+
+    int dev_count = 0;
+    SGM_CUDA(cudaGetDeviceCount(&dev_count));
+    if (device < 0 || device >= dev_count) return sgm_fail(SGM_ERR_INVALID, "plan_create: bad device");
+    SGM_CUDA(cudaSetDevice(device));
+    sgm_plan* plan = new sgm_plan();
+    plan->device = device;
+    cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    plan->n_vals = desc->map_off[T];
+    plan->corners = corners;
+    plan->kmax = kmax;
+    PlanDev& d = plan->dev;
+    d.kind = kind; d.N = N; d.E = (int)entries.size(); d.B = B; d.T = (int)T;
+    d.n_knots = (int)n_knots;
+
+    std::vector<double> coeff(desc->coeffs, desc->coeffs + T);
+    std::vector<int> maps(desc->maps, desc->maps + desc->map_off[T]);
+    std::vector<double> knots(desc->fam_knots, desc->fam_knots + n_knots);
+    std::vector<double> lambda;
+    if (kind == SGM_LAGRANGE) lambda.assign(desc->fam_lambda, desc->fam_lambda + n_knots);
+    std::vector<unsigned> flags(4, 0u);
+    int rc = SGM_OK;
+    const unsigned* cflags = nullptr;
+    if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
+        (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
+        (rc = upload(plan, maps, &d.maps)) || (rc = upload(plan, knots, &d.knots)) ||
+        (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, flags, &cflags))) {
+        sgm_plan_destroy(plan);
+        return rc;
+    }
+    d.flags = const_cast<unsigned*>(cflags);
+    *out = plan;
+    return SGM_OK;
+}
+
+void sgm_plan_destroy(sgm_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    for (void* p : plan->allocations) cudaFree(p);
+    delete plan;
+}
+
+int64_t sgm_plan_table_bytes(const sgm_plan* plan) { return plan ? plan->table_bytes : 0; }
+int64_t sgm_plan_corners_per_point(const sgm_plan* plan) { return plan ? plan->corners : 0; }
+
+int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags) {
+    if (!plan || !flags) return sgm_fail(SGM_ERR_INVALID, "take_flags: null argument");
+    SGM_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned host = 0;
+    SGM_CUDA(cudaMemcpyAsync(&host, plan->dev.flags, sizeof host, cudaMemcpyDeviceToHost, s));
+    SGM_CUDA(cudaMemsetAsync(plan->dev.flags, 0, sizeof host, s));
+    SGM_CUDA(cudaStreamSynchronize(s));
+    *flags = host;
+    return SGM_OK;
+}
+
+size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
+    if (!plan || NF != 1) return 256;
+    size_t bytes = align_up((size_t)plan->n_vals * 8, 256);
+    const PointLaunch L = choose_point_launch(plan);
+    if (L.global_basis) {
+        const int64_t tiles = (P + L.threads - 1) / std::max(L.threads, 1);
+        const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+        bytes += (size_t)std::max<int64_t>(blocks, 1) * L.threads *
+                 ((size_t)plan->dev.B * 8 + (size_t)plan->dev.E * 2);
+    }
+    return bytes + 256;
+}
+
+int sgm_eval(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t M,
+             int64_t NF, int64_t ldf, double* out, int64_t ldo, void* workspace,
+             size_t workspace_bytes, void* stream) {
+    return eval_one(plan, x, P, ldx, f, M, NF, ldf, out, ldo, 1.0, 0, workspace, workspace_bytes,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_parts,
+                        const double* x, int64_t P, int64_t ldx, const double* const* f,
+                        const int64_t* M, const int64_t* ldf, int64_t NF, double* out, int64_t ldo,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plans || !signs || !f || !M || !ldf || n_parts < 1)
+        return sgm_fail(SGM_ERR_INVALID, "eval_signed_sum: null argument");
+    for (int i = 0; i < n_parts; ++i) {
+        int rc = eval_one(plans[i], x, P, ldx, f[i], M[i], NF, ldf[i], out, ldo, signs[i], i > 0,
+                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    }
+    return SGM_OK;
+}
+
+int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, int32_t d,
+                    int64_t ldy, double T, double sqrtT, const double* level_scale, int32_t L,
+                    double* W, int64_t ldw, void* stream) {
+    if (nt < 0 || P < 0 || d < 1 || ldy < d || ldw < nt || L < 0 || L > 40)
+        return sgm_fail(SGM_ERR_INVALID, "lc_brownian: bad shapes");
+    if (nt == 0 || P == 0) return SGM_OK;
+    if (!tt || !yy || !W || (L > 0 && !level_scale))
+        return sgm_fail(SGM_ERR_INVALID, "lc_brownian: null buffer");
+    int dev = 0, sms = 148;
+    SGM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t total = P * nt;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+    sgm::lc_brownian_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+int sgm_kl_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, int32_t d,
+                    int64_t ldy, const double* factor, const double* freq, double* W,
+                    int64_t ldw, void* stream) {
+    if (nt < 0 || P < 0 || d < 0 || ldy < d || ldw < nt)
+        return sgm_fail(SGM_ERR_INVALID, "kl_brownian: bad shapes");
+    if (nt == 0 || P == 0) return SGM_OK;
+    if (!tt || !yy || !W || (d > 0 && (!factor || !freq)))
+        return sgm_fail(SGM_ERR_INVALID, "kl_brownian: null buffer");
+    int dev = 0, sms = 148;
+    SGM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t total = P * nt;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+    sgm::kl_brownian_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        tt, nt, yy, P, d, ldy, factor, freq, W, ldw);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// sgm_kernels.cuh -- fp64 evaluation kernels for combination-technique sparse-grid
+// interpolants on sm_100a.  No tensor cores: the path is gather / FP64-issue bound (see
+// DESIGN.md).  The file is compiled with -fmad=false so that every product and sum is
+// rounded separately, in the order of the reference's numpy / scipy arithmetic:
+//
+//   per term t (reference order):   tp = 0
+//       per corner / node in C order: w = ((1*b_0)*b_1)*...   (directions ascending)
+//                                     tp = tp + value * w
+//   out = out + c_t * tp
+//
+// Reference semantics implemented here (paths under /root/reference/sgmethods):
+//   fill_basis<LINEAR>     scipy find_indices + norm distances, called from
+//                          tp_inteprolants.py:49-53 (RegularGridInterpolator, extrapolating)
+//   fill_basis<QUADRATIC>  tp_inteprolants.py:100-136
+//   fill_basis<CUBIC>      tp_inteprolants.py:206-253
+//   fill_basis<LAGRANGE>   tp_inteprolants.py:339-346 (lambda from :311-320, host-computed)
+//   term walk              sparse_grid_interpolant.py:268-279, tp_interpolant_wrapper.py:54-64
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/sgm_b200.h"
+
+namespace sgm {
+
+struct TermHdr { int k; int dim_off; int val_off; int ncorner; };   // 16 B, one per term
+struct TermDim { int boff; int stride; int radix; int ent; };       // 16 B, one per active dir
+struct Entry   { int dim; int knot_off; int n; int boff; };         // one per (direction, knots)
+
+// Device view of a plan (passed by value to the kernels).
+struct PlanDev {
+    int kind, N, E, B;                 // B = basis doubles per point
+    int T;
+    int n_knots;                       // doubles in `knots` (and `lambda`)
+    const TermHdr* hdr;
+    const TermDim* tdim;
+    const double* coeff;
+    const Entry* ent;
+    const int* maps;
+    const double* knots;
+    const double* lambda;
+    unsigned* flags;
+};
+
+// ---------------------------------------------------------------------------------------
+// 1-D basis tables.  `bas[b * bs]` / `idx[e * bs]` address the slot of this point.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int count_le(const double* g, int n, double x) {
+    int lo = 0, hi = n;                          // #{i : g[i] <= x}; NaN -> 0
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (g[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int count_lt_strided(const double* g, int nh, int q, double x) {
+    int lo = 0, hi = nh;                         // #{i : g[i*q] < x}; NaN -> 0
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (g[mid * q] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int KIND, typename IdxT>
+__device__ __forceinline__ void fill_basis(const Entry e, double x, const double* __restrict__ knots,
+                                           const double* __restrict__ lambda, double* bas,
+                                           IdxT* idx, int ent_id, int bs, unsigned* flags) {
+    const double* g = knots + e.knot_off;
+    const int n = e.n;
+    double* b = bas + (size_t)e.boff * bs;
+    if (KIND == SGM_PW_LINEAR) {
+        int i = count_le(g, n, x) - 1;
+        i = max(0, min(i, n - 2));
+        b[0] = (x - g[i]) / (g[i + 1] - g[i]);
+        idx[(size_t)ent_id * bs] = (IdxT)i;
+    } else if (KIND == SGM_PW_QUADRATIC) {
+        const int H = (n + 1) >> 1;
+        int j = max(count_lt_strided(g, H, 2, x) - 1, 0);
+        if (j > H - 2 || x != x) {
+            // the reference indexes past the knot vector here -> IndexError
+            atomicOr(flags, SGM_FLAG_QUADRATIC_RIGHT);
+            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+            b[0] = qnan; b[bs] = qnan; b[2 * bs] = qnan;
+            idx[(size_t)ent_id * bs] = (IdxT)0;
+            return;
+        }
+        const double x0 = g[2 * j], x1 = g[2 * j + 1], x2 = g[2 * j + 2];
+        b[0]      = ((x - x1) * (x - x2)) / ((x0 - x1) * (x0 - x2));
+        b[bs]     = ((x - x0) * (x - x2)) / ((x1 - x0) * (x1 - x2));
+        b[2 * bs] = ((x - x0) * (x - x1)) / ((x2 - x0) * (x2 - x1));
+        idx[(size_t)ent_id * bs] = (IdxT)(2 * j);
+    } else if (KIND == SGM_PW_CUBIC) {
+        const int H = (n + 2) / 3;
+        int j = count_lt_strided(g, H, 3, x) - 1;
+        if (x != x) j = H - 2;                    // NaN sorts last in the reference
+        j = max(0, min(j, H - 2));
+        const double x0 = g[3 * j], x1 = g[3 * j + 1], x2 = g[3 * j + 2], x3 = g[3 * j + 3];
+        b[0]      = ((x - x1) * (x - x2) * (x - x3)) / ((x0 - x1) * (x0 - x2) * (x0 - x3));
+        b[bs]     = ((x - x0) * (x - x2) * (x - x3)) / ((x1 - x0) * (x1 - x2) * (x1 - x3));
+        b[2 * bs] = ((x - x0) * (x - x1) * (x - x3)) / ((x2 - x0) * (x2 - x1) * (x2 - x3));
+        b[3 * bs] = ((x - x0) * (x - x1) * (x - x2)) / ((x3 - x0) * (x3 - x1) * (x3 - x2));
+        idx[(size_t)ent_id * bs] = (IdxT)(3 * j);
+    } else {
+        const double* lam = lambda + e.knot_off;
+        double ell = x - g[0];
+        for (int r = 1; r < n; ++r) ell = ell * (x - g[r]);
+        for (int i = 0; i < n; ++i) b[(size_t)i * bs] = (ell * lam[i]) / (x - g[i]);
+        idx[(size_t)ent_id * bs] = (IdxT)0;
+    }
+}
+
+// weight of digit `a` in the direction described by `d`
+template <int KIND>
+__device__ __forceinline__ double digit_weight(const double* bas, int bs, const TermDim d, int a) {
+    if (KIND == SGM_PW_LINEAR) {
+        const double y = bas[(size_t)d.boff * bs];
+        return a ? y : 1.0 - y;
+    }
+    return bas[(size_t)(d.boff + a) * bs];
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A: one thread per point, scalar output (NF == 1).  G holds the node values already
+// gathered per term (G[val_off + c_order_index]), so a corner is one dependent load.
+// Basis tables live in shared memory ([b][thread], conflict-free) or, when they do not fit,
+// in a per-block global scratch with the same layout (coalesced, L2 resident).
+// ---------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ double linear_term(const TermDim* __restrict__ td, const double* bas,
+                                              const unsigned short* idx, int bs,
+                                              const double* __restrict__ Gt) {
+    double wl[K], wh[K];
+    int st[K];
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const TermDim d = td[j];
+        const double y = bas[(size_t)d.boff * bs];
+        wh[j] = y;
+        wl[j] = 1.0 - y;
+        st[j] = d.stride;
+        base += (int)idx[(size_t)d.ent * bs] * d.stride;
+    }
+    double tp = 0.0;
+#pragma unroll
+    for (int c = 0; c < (1 << K); ++c) {
+        double w = 1.0;
+        int off = base;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int bit = (c >> (K - 1 - j)) & 1;
+            w = w * (bit ? wh[j] : wl[j]);
+            off += bit ? st[j] : 0;
+        }
+        tp = tp + Gt[off] * w;
+    }
+    return tp;
+}
+
+template <int KIND>
+__device__ __noinline__ double generic_term(const TermHdr h, const TermDim* __restrict__ td,
+                                            const double* bas, const unsigned short* idx, int bs,
+                                            const double* __restrict__ Gt) {
+    double tp = 0.0;
+    for (int c = 0; c < h.ncorner; ++c) {
+        double w = 1.0;
+        int off = 0;
+        int cs = h.ncorner;
+        for (int j = 0; j < h.k; ++j) {
+            const TermDim d = td[j];
+            cs /= d.radix;
+            const int a = (c / cs) % d.radix;
+            w = w * digit_weight<KIND>(bas, bs, d, a);
+            off += ((int)idx[(size_t)d.ent * bs] + a) * d.stride;
+        }
+        tp = tp + Gt[off] * w;
+    }
+    return tp;
+}
+
+template <int KIND, bool GLOBAL_BASIS>
+__global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
+                                   int64_t ldx, const double* __restrict__ G,
+                                   double* __restrict__ out, int64_t ldo, double scale,
+                                   int accumulate, unsigned char* __restrict__ gscratch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int bs = blockDim.x;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = tid; i < pl.n_knots; i += bs) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+    }
+    unsigned char* after = reinterpret_cast<unsigned char*>(
+        sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots);
+    double* bas;
+    unsigned short* idx;
+    if (GLOBAL_BASIS) {
+        const size_t per_block = ((size_t)pl.B * 8 + (size_t)pl.E * 2) * bs;
+        unsigned char* mine = gscratch + (size_t)blockIdx.x * per_block;
+        bas = reinterpret_cast<double*>(mine) + tid;
+        idx = reinterpret_cast<unsigned short*>(mine + (size_t)pl.B * 8 * bs) + tid;
+    } else {
+        bas = reinterpret_cast<double*>(after) + tid;
+        idx = reinterpret_cast<unsigned short*>(after + (size_t)pl.B * 8 * bs) + tid;
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (P + bs - 1) / bs;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p = tile * bs + tid;
+        if (p >= P) continue;                        // no block-level sync below
+        const double* xp = x + p * ldx;
+        for (int e = 0; e < pl.E; ++e) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas, idx, e, bs,
+                                             pl.flags);
+        }
+        double acc = 0.0;
+        for (int t = 0; t < pl.T; ++t) {
+            const TermHdr h = pl.hdr[t];
+            const double c = pl.coeff[t];
+            const TermDim* td = pl.tdim + h.dim_off;
+            const double* Gt = G + h.val_off;
+            double tp;
+            if (h.k == 0) {
+                tp = Gt[0];
+            } else if (KIND == SGM_PW_LINEAR && h.k <= 4) {
+                switch (h.k) {
+                    case 1: tp = linear_term<1>(td, bas, idx, bs, Gt); break;
+                    case 2: tp = linear_term<2>(td, bas, idx, bs, Gt); break;
+                    case 3: tp = linear_term<3>(td, bas, idx, bs, Gt); break;
+                    default: tp = linear_term<4>(td, bas, idx, bs, Gt); break;
+                }
+            } else {
+                tp = generic_term<KIND>(h, td, bas, idx, bs, Gt);
+            }
+            acc = acc + c * tp;
+        }
+        double* o = out + p * ldo;
+        if (accumulate) *o = *o + scale * acc;
+        else *o = (scale == 1.0) ? acc : scale * acc;
+    }
+}
+
+// G[j, 0:NF] = f[maps[j], 0:NF]  (the reference's per-term fancy-index copy,
+// sparse_grid_interpolant.py:274, done once for all terms)
+__global__ void pregather_kernel(const int* __restrict__ maps, int64_t n_vals,
+                                 const double* __restrict__ f, int64_t ldf, int64_t NF,
+                                 double* __restrict__ G) {
+    const int64_t total = n_vals * NF;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = i / NF, c = i - j * NF;
+        G[i] = f[(int64_t)maps[j] * ldf + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel B: vector-valued output.  One warp per point, lanes across output columns
+// (coalesced row-segment gathers of f_on_SG through the node map), CPL columns per lane.
+// The 32 lanes first compute the weights and rows of 32 corners in parallel, then the
+// warp walks them in reference order, sharing weight and row by shuffles.
+// ---------------------------------------------------------------------------------------
+template <int KIND, int CPL>
+__global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
+                                 int64_t ldx, const double* __restrict__ f, int64_t ldf,
+                                 int64_t NF, double* __restrict__ out, int64_t ldo,
+                                 double scale, int accumulate, int pts_per_block) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+    }
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* bas = sbas_all + (size_t)warp * pl.B;
+    int* idx = reinterpret_cast<int*>(sbas_all + (size_t)n_warps * pl.B) + (size_t)warp * pl.E;
+    __syncthreads();
+
+    const int64_t col0 = (int64_t)blockIdx.y * (32 * CPL) + lane;
+    const int64_t p_begin = (int64_t)blockIdx.x * pts_per_block;
+    const int64_t p_end = min(P, p_begin + pts_per_block);
+    for (int64_t p = p_begin + warp; p < p_end; p += n_warps) {
+        const double* xp = x + p * ldx;
+        __syncwarp();
+        for (int e = lane; e < pl.E; e += 32) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, int>(en, xp[en.dim], sknots, slambda, bas, idx, e, 1, pl.flags);
+        }
+        __syncwarp();
+        double acc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+        for (int t = 0; t < pl.T; ++t) {
+            const TermHdr h = pl.hdr[t];
+            const double coef = pl.coeff[t];
+            const TermDim* td = pl.tdim + h.dim_off;
+            const int* tmap = pl.maps + h.val_off;
+            double tp[CPL];
+            if (h.k == 0) {
+                const double* fr = f + (int64_t)tmap[0] * ldf;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int64_t col = col0 + 32 * c;
+                    tp[c] = col < NF ? fr[col] : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) tp[c] = 0.0;
+                for (int c_base = 0; c_base < h.ncorner; c_base += 32) {
+                    const int cid = c_base + lane;
+                    double w = 1.0;
+                    int row = 0;
+                    if (cid < h.ncorner) {
+                        int off = 0;
+                        int cs = h.ncorner;
+                        for (int j = 0; j < h.k; ++j) {
+                            const TermDim d = td[j];
+                            cs /= d.radix;
+                            const int a = (cid / cs) % d.radix;
+                            w = w * digit_weight<KIND>(bas, 1, d, a);
+                            off += (idx[d.ent] + a) * d.stride;
+                        }
+                        row = tmap[off];
+                    }
+                    const int n_in = min(32, h.ncorner - c_base);
+                    for (int cc = 0; cc < n_in; ++cc) {
+                        const double wv = __shfl_sync(0xffffffffu, w, cc);
+                        const int r = __shfl_sync(0xffffffffu, row, cc);
+                        const double* fr = f + (int64_t)r * ldf;
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) {
+                            const int64_t col = col0 + 32 * c;
+                            if (col < NF) tp[c] = tp[c] + fr[col] * wv;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] = acc[c] + coef * tp[c];
+        }
+        double* o = out + p * ldo;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int64_t col = col0 + 32 * c;
+            if (col < NF) {
+                if (accumulate) o[col] = o[col] + scale * acc[c];
+                else o[col] = (scale == 1.0) ? acc[c] : scale * acc[c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Brownian-motion expansions (parametric_expansions_brownian_motion.py:17-91)
+// ---------------------------------------------------------------------------------------
+// One hat per level contains s = t/T; all other hats of the level contribute an exact 0 in
+// the reference's O(d) sum, so accumulating only that hat, level by level, gives the same
+// bits.
+__global__ void lc_brownian_kernel(const double* __restrict__ tt, int64_t nt,
+                                   const double* __restrict__ yy, int64_t P, int d, int64_t ldy,
+                                   double T, double sqrtT, const double* __restrict__ level_scale,
+                                   int L, double* __restrict__ W, int64_t ldw) {
+    const int64_t total = P * nt;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / nt, it = i - p * nt;
+        const double* y = yy + p * ldy;
+        const double s = tt[it] / T;
+        double w = y[0] * s;
+        if (s >= 0.0 && s <= 1.0) {
+            for (int l = 1; l <= L; ++l) {
+                const int64_t half = (int64_t)1 << (l - 1);          // hats on this level
+                const double inv = 1.0 / (double)(half << 1);        // 2^-l, exact
+                int64_t j = (int64_t)floor(s * (double)half);
+                if (j > half - 1) j = half - 1;
+                const int64_t k = half + j;                          // coefficient index
+                if (k >= d) continue;                                // zero padding
+                const double left = (double)(2 * j) * inv;
+                const double mid = (double)(2 * j + 1) * inv;
+                const double right = (double)(2 * j + 2) * inv;
+                const double eta = (s >= mid) ? (-s + right) : (s - left);
+                w = w + (y[k] * level_scale[l - 1]) * eta;
+            }
+        }
+        W[p * ldw + it] = w * sqrtT;
+    }
+}
+
+__global__ void kl_brownian_kernel(const double* __restrict__ tt, int64_t nt,
+                                   const double* __restrict__ yy, int64_t P, int d, int64_t ldy,
+                                   const double* __restrict__ factor,
+                                   const double* __restrict__ freq, double* __restrict__ W,
+                                   int64_t ldw) {
+    const int64_t total = P * nt;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / nt, it = i - p * nt;
+        const double* y = yy + p * ldy;
+        const double t = tt[it];
+        double w = 0.0 * t;
+        for (int n = 0; n < d; ++n) w = w + (factor[n] * sin(freq[n] * t)) * y[n];
+        W[p * ldw + it] = w;
+    }
+}
+
+}  // namespace sgm

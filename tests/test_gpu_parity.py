@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C ABI) with the reference -- needs a B200.
+
+Sources of truth, in this order:
+  1. tests/golden/*.npz: outputs of the unmodified reference on seeded inputs;
+  2. the CPU oracle (oracle/), itself pinned to (1), on fresh seeded inputs;
+  3. size-independent properties at BASELINE sizes (interpolation at the nodes, partition of
+     unity, linearity in the nodal values).
+Tolerance (BASELINE.json north_star): max|gpu - ref| / max|ref| <= 1e-12 in fp64.  The
+kernels reproduce the reference's operation order, so most results are bit-identical; the
+bit-exact fraction is printed for information.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from golden_cases import CASES, LEV2KNOTS, knot_family
+from oracle import brownian_oracle, sg_oracle
+from sgmethods_b200 import multi_index_sets as mis, nodes_1d
+from sgmethods_b200.parametric_expansions_brownian_motion import (param_KL_Brownian_motion,
+                                                                   param_LC_Brownian_motion)
+from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
+from sgmethods_b200.tp_inteprolants import (TPLagrangeInterpolator, TPPwCubicInterpolator,
+                                            TPPwLinearInterpolator, TPPwQuadraticInterpolator)
+
+pytestmark = pytest.mark.gpu
+TOL = 1.e-12
+KIND_CLASS = {"linear": TPPwLinearInterpolator, "quadratic": TPPwQuadraticInterpolator,
+              "cubic": TPPwCubicInterpolator, "lagrange": TPLagrangeInterpolator}
+
+
+def rel_err(got, ref):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    if not ok.any():
+        return 0.0
+    scale = np.max(np.abs(ref[ok]))
+    return float(np.max(np.abs(got[ok] - ref[ok])) / (scale if scale > 0 else 1.0))
+
+
+def oracle_plan_of(it):
+    return sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
+                                      it.active_tp_nodes_list, it.map_tp_to_SG)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_reference_outputs(name):
+    fam, l2k, kind = CASES[name]
+    g = load_golden(name)
+    it = SGInterpolant(g["mid_set"], knot_family(fam, nodes_1d), LEV2KNOTS[l2k],
+                       tp_interpolant=KIND_CLASS[kind], verbose=False)
+    out = it.interpolate(g["x"], g["f_on_SG"])
+    err = rel_err(out, g["out"])
+    ok = ~np.isnan(g["out"])
+    exact = np.mean(out[ok] == g["out"][ok])
+    print(f"{name}: rel err {err:.2e}, bit-exact {100 * exact:.1f}%")
+    assert err <= TOL
+
+
+def test_lambda_factory_and_sampling_like_reference_test():
+    """tests/test_sparse_grid_interpolant.py:60-106 (operator passed as a lambda factory)."""
+    N = 4
+    F = lambda x: np.exp(np.sum(x))  # noqa: E731
+    np.random.seed(0)
+    pts = np.random.uniform(-1, 1, [5000, N])
+    f_rnd = np.array(list(map(F, pts)))
+    errs, nodes = [], []
+    for w in range(7):
+        it = SGInterpolant(mis.smolyak_mid_set(w, N=N), nodes_1d.cc_nodes, lambda nu: nu + 1,
+                           tp_interpolant=lambda n, f: TPPwLinearInterpolator(n, f),
+                           n_parallel=1, verbose=False)
+        f_on_SG = it.sample_on_SG(F)
+        val = it.interpolate(pts, f_on_SG)
+        errs.append(np.amax(np.abs(val - f_rnd)))
+        nodes.append(it.num_nodes)
+        if w == 3:      # same arithmetic as the CPU path
+            ref = sg_oracle.interpolate(oracle_plan_of(it), pts[:512], f_on_SG)
+            assert rel_err(val[:512], ref) <= TOL
+    errs, nodes = np.array(errs), np.array(nodes, dtype=float)
+    assert np.all(np.diff(nodes) > 0) and np.all(np.diff(errs) < 0)
+    assert np.all(errs < 31 * nodes ** 0.02 * np.exp(-0.005 * nodes))
+
+
+def test_exactness_tests_of_the_reference():
+    """tests/test_sparse_grid_interpolant.py:15-57: degree-1 (linear) and degree-3 (cubic)."""
+    P1 = lambda x: 2. + x[0] + x[0] * x[1]  # noqa: E731
+    Lam = np.array([[0, 0], [0, 1], [1, 0], [1, 1]])
+    it = SGInterpolant(Lam, nodes_1d.equispaced_nodes, lambda n: n + 1, verbose=False)
+    x = np.random.default_rng(0).uniform(-1, 1, [10, 2])
+    got = it.interpolate(x, it.sample_on_SG(P1))
+    assert np.linalg.norm(got - np.array([P1(r) for r in x])) < 1.e-4
+    P3 = lambda x: 2. + x[0] + x[0] * x[1] + x[1] ** 3 + x[0] * x[1] ** 3  # noqa: E731
+    Lam = np.array([[0, 0], [0, 1], [0, 2], [0, 3], [1, 0], [1, 1], [1, 2], [1, 3]])
+    it = SGInterpolant(Lam, nodes_1d.equispaced_nodes, lambda n: 3 * n + 1,
+                       tp_interpolant=TPPwCubicInterpolator, verbose=False)
+    got = it.interpolate(x, it.sample_on_SG(P3))
+    assert np.linalg.norm(got - np.array([P3(r) for r in x])) < 1.e-4
+
+
+@pytest.mark.parametrize("kind,NF", [("linear", 1), ("linear", 7), ("linear", 200),
+                                     ("quadratic", 1), ("quadratic", 40), ("cubic", 1),
+                                     ("cubic", 33), ("lagrange", 1), ("lagrange", 130)])
+def test_fresh_inputs_against_oracle(kind, NF):
+    rng = np.random.default_rng(100 + NF)
+    if kind == "cubic":
+        S, knots, lev = mis.smolyak_mid_set(3, 4), nodes_1d.equispaced_nodes, (lambda n: 3 * n + 1)
+        x = rng.uniform(-1.4, 1.4, (300, 4))
+    elif kind == "lagrange":
+        S, knots, lev = mis.smolyak_mid_set(3, 4), nodes_1d.hermite_nodes, (lambda n: 2 * n + 1)
+        x = rng.normal(0, 1, (300, 4))
+    elif kind == "quadratic":
+        S, knots = mis.aniso_smolyak_mid_set(4, 5, [1, 1, 1.5, 2, 2]), nodes_1d.cc_nodes
+        lev = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa: E731
+        x = rng.uniform(-1, 1, (300, 5))
+    else:
+        S, knots, lev = mis.smolyak_mid_set(4, 6), nodes_1d.unbounded_nodes_nested, (lambda n: 2 ** (n + 1) - 1)
+        x = rng.normal(0, 1.3, (300, 6))
+    it = SGInterpolant(S, knots, lev, tp_interpolant=KIND_CLASS[kind], verbose=False)
+    f = rng.normal(size=(it.num_nodes, NF))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x, f, kind, squeeze=False)
+    got = it.interpolate(x, f).reshape(ref.shape)
+    err = rel_err(got, ref)
+    print(f"{kind} NF={NF}: T={len(it.combination_coeffs)} M={it.num_nodes} rel err {err:.2e} "
+          f"bit-exact {100 * np.mean(got == ref):.1f}%")
+    assert err <= TOL
+
+
+def test_smooth_function_with_large_coefficients():
+    """Cancellation check: smooth f, |c| up to 1e3; the GPU result must be
+    within 1e-12 of the CPU arithmetic although sum|c| ~ 4e4."""
+    S = mis.smolyak_mid_set(4, 16)
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1,
+                       verbose=False)
+    assert len(it.combination_coeffs) == 4845 and it.num_nodes == 69121
+    w = 1.0 / np.arange(1, 17) ** 2
+    f = np.sin(it.SG @ w).reshape(-1, 1)
+    x = np.random.default_rng(0).normal(size=(1024, 16))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x, f)
+    got = it.interpolate(x, f)
+    err = rel_err(got, ref)
+    print(f"C2 shape smooth f: rel err {err:.2e}, bit-exact {100 * np.mean(got == ref):.1f}%")
+    assert err <= TOL
+
+
+def test_properties_at_config2_size():
+    """BASELINE config 2 (d=16, smolyak w=4, 10^6 points): properties that need no CPU run."""
+    import torch
+    S = mis.smolyak_mid_set(4, 16)
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1,
+                       verbose=False)
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn((10 ** 6, 16), dtype=torch.float64, device=dev, generator=gen)
+    f1 = torch.randn((it.num_nodes, 1), dtype=torch.float64, device=dev, generator=gen)
+    f2 = torch.randn((it.num_nodes, 1), dtype=torch.float64, device=dev, generator=gen)
+    o1, o2 = it.interpolate(x, f1), it.interpolate(x, f2)
+    o12 = it.interpolate(x, 2.0 * f1 - 3.0 * f2)
+    scale = float(o12.abs().max())
+    assert float((o12 - (2.0 * o1 - 3.0 * o2)).abs().max()) <= 1e-11 * scale   # linearity
+    ones = it.interpolate(x, torch.ones_like(f1))
+    assert float((ones - 1.0).abs().max()) <= 1e-9                             # sum c_t = 1
+    # nested knots: the interpolant reproduces the nodal values at the sparse-grid nodes
+    nodes = torch.from_numpy(it.SG).to(dev)
+    at_nodes = it.interpolate(nodes, f1)
+    assert float((at_nodes - f1[:, 0]).abs().max()) <= 1e-9 * float(f1.abs().max()) * 1e3
+    # determinism
+    assert torch.equal(o1, it.interpolate(x, f1))
+
+
+def test_torch_tensors_in_torch_tensor_out_and_extra_columns():
+    import torch
+    g = load_golden("lin_example1")
+    fam, l2k, kind = CASES["lin_example1"]
+    it = SGInterpolant(g["mid_set"], knot_family(fam, nodes_1d), LEV2KNOTS[l2k], verbose=False)
+    x = torch.from_numpy(g["x"]).cuda()                       # 1000 columns, 10 used
+    out = it.interpolate(x, torch.from_numpy(g["f_on_SG"]).cuda())
+    assert out.is_cuda and out.shape == (32,)
+    assert rel_err(out.cpu().numpy(), g["out"]) <= TOL
+    with pytest.raises(IndexError):
+        it.interpolate(g["x"][:, :5], g["f_on_SG"])            # too few columns
+
+
+def test_quadratic_right_of_last_knot_raises_index_error():
+    it = SGInterpolant(mis.smolyak_mid_set(2, 2), nodes_1d.cc_nodes,
+                       lambda n: np.where(n == 0, 1, 2 ** n + 1),
+                       tp_interpolant=TPPwQuadraticInterpolator, verbose=False)
+    f = np.ones((it.num_nodes, 1))
+    assert np.allclose(it.interpolate(np.array([[0.2, -1.5], [1.0, 1.0]]), f), 1.0)
+    with pytest.raises(IndexError):
+        it.interpolate(np.array([[0.2, 1.0000001]]), f)
+    with pytest.raises(IndexError):
+        it.interpolate(np.array([[np.nan, 0.0]]), f)
+    assert np.allclose(it.interpolate(np.array([[0.2, 0.3]]), f), 1.0)   # flag was cleared
+
+
+def test_cubic_with_three_knots_raises_like_reference():
+    it = SGInterpolant(mis.smolyak_mid_set(1, 2), nodes_1d.equispaced_nodes,
+                       lambda n: 2 * n + 1, tp_interpolant=TPPwCubicInterpolator, verbose=False)
+    with pytest.raises(UnboundLocalError):
+        it.interpolate(np.zeros((2, 2)), np.ones((it.num_nodes, 1)))
+
+
+def test_lagrange_on_a_knot_is_nan_like_reference():
+    it = SGInterpolant(mis.smolyak_mid_set(2, 2), nodes_1d.hermite_nodes, lambda n: 2 * n + 1,
+                       tp_interpolant=TPLagrangeInterpolator, verbose=False)
+    out = it.interpolate(np.array([[0.0, 0.3], [0.1, 0.3]]), np.ones((it.num_nodes, 1)))
+    assert np.isnan(out[0]) and abs(out[1] - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("cls,op", [(TPPwLinearInterpolator, "linear"),
+                                    (TPPwQuadraticInterpolator, "quadratic"),
+                                    (TPPwCubicInterpolator, "cubic"),
+                                    (TPLagrangeInterpolator, "lagrange")])
+def test_standalone_operators_follow_the_plugin_protocol(cls, op):
+    """cls(nodes_tuple, f_on_nodes)(x_new) -> (P, dim_f) (tp_inteprolants.py:1-11), with a
+    different knot vector per direction and the same node count in two directions."""
+    rng = np.random.default_rng(11)
+    nodes = (np.linspace(-1, 1, 7), np.sort(rng.uniform(-1, 1, 7)), np.linspace(-1, 1, 4))
+    if op == "quadratic":
+        nodes = nodes[:2] + (np.linspace(-1, 1, 5),)
+    vals = rng.normal(size=tuple(n.size for n in nodes) + (3,))
+    x = rng.uniform(-1, 1, (200, 3))
+    if op == "quadratic":
+        x[:, 1] = np.minimum(x[:, 1], nodes[1][-1])
+    got = cls(nodes, vals)(x)
+    ref = sg_oracle.OPERATORS[op](nodes, vals, x)
+    assert got.shape == (200, 3) and rel_err(got, ref) <= TOL
+    scalar = cls(nodes, vals[..., 0])(x)                       # scalar field: (P, 1)
+    assert scalar.shape == (200, 1) and rel_err(scalar[:, 0], ref[:, 0]) <= TOL
+
+
+def test_levy_ciesielski_bit_exact_against_reference_outputs():
+    g = load_golden("brownian")
+    W = param_LC_Brownian_motion(g["lc64_tt"], g["lc64_yy"], 1)
+    assert W.shape == g["lc64_W"].shape and np.array_equal(W, g["lc64_W"])
+    W = param_LC_Brownian_motion(g["lc5_tt"], g["lc5_yy"], 2.0)
+    assert np.array_equal(W, g["lc5_W"])
+    W = param_LC_Brownian_motion(g["lc5_tt"], g["lc1_yy"], 2.0)
+    assert np.array_equal(W, g["lc1_W"])
+    one = param_LC_Brownian_motion(g["lc64_tt"], g["lc64_yy"][0], 1)      # 1-D in, 1-D out
+    assert one.shape == (1001,) and np.array_equal(one, g["lc64_W"][0])
+    with pytest.warns(UserWarning):
+        param_LC_Brownian_motion(np.array([0.0, 1.5]), g["lc5_yy"][0], 1.0)
+
+
+def test_levy_ciesielski_large_batch_against_oracle():
+    rng = np.random.default_rng(2)
+    tt = np.linspace(0, 1, 2000)
+    yy = rng.normal(size=(500, 64))
+    W = param_LC_Brownian_motion(tt, yy, 1.0)
+    for p in (0, 17, 499):
+        assert np.array_equal(W[p], brownian_oracle.lc_brownian(tt, yy[p], 1.0))
+
+
+def test_karhunen_loeve_against_reference_outputs():
+    g = load_golden("brownian")
+    W = param_KL_Brownian_motion(g["kl_tt"], g["kl_yy"])
+    assert rel_err(W, g["kl_W"]) <= TOL
