@@ -39,6 +39,7 @@ using sgm::Entry;
 using sgm::PlanDev;
 using sgm::TermDim;
 using sgm::TermHdr;
+using sgm::TermRec;
 
 struct sgm_plan {
     int device = 0;
@@ -111,6 +112,57 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
         if (fixed <= cap) return PointLaunch{128, fixed, true, 4};
     }
     return best;
+}
+
+// Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
+struct SplitLaunch { int warps; int chunk; size_t smem; int blocks_per_sm; };
+
+template <int KIND>
+SplitLaunch choose_split_launch(const sgm_plan* plan) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1) +
+                         (size_t)d.B * 32 * 8 + (size_t)d.E * 32 * 2 + 32 * 8 + 64;
+    SplitLaunch best{0, 0, 0, 0};
+    int best_warps = 0;
+    const int cand[4][2] = {{16, 64}, {8, 32}, {8, 64}, {4, 32}};
+    for (const auto& c : cand) {
+        const size_t smem = fixed + 2 * (size_t)c[1] * 32 * 8;
+        if (smem > (size_t)plan->max_smem_optin) continue;
+        auto kern = sgm::eval_points_split_kernel<KIND>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            continue;
+        int bps = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, c[0] * 32, smem) != cudaSuccess)
+            continue;
+        if (bps * c[0] > best_warps) {
+            best_warps = bps * c[0];
+            best = SplitLaunch{c[0], c[1], smem, bps};
+        }
+    }
+    return best;
+}
+
+template <int KIND>
+int launch_points(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
+                  double* out, int64_t ldo, double scale, int accumulate, unsigned char* scratch,
+                  size_t scratch_bytes, cudaStream_t stream);
+
+template <int KIND>
+int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
+                        double* out, int64_t ldo, double scale, int accumulate,
+                        unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    const SplitLaunch L = choose_split_launch<KIND>(plan);
+    if (L.warps == 0 || L.blocks_per_sm * L.warps < 8)      // tables too large: thread-per-point
+        return launch_points<KIND>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch,
+                                   scratch_bytes, stream);
+    const int64_t tiles = (P + 31) / 32;
+    const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+    auto kern = sgm::eval_points_split_kernel<KIND>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+                                                            scale, accumulate, L.chunk);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
 }
 
 template <int KIND>
@@ -197,10 +249,10 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         SGM_CUDA(cudaGetLastError());
         const size_t sb = workspace_bytes - g_bytes;
         switch (kind) {
-            case SGM_PW_LINEAR: return launch_points<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            case SGM_PW_QUADRATIC: return launch_points<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            case SGM_PW_CUBIC: return launch_points<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            default: return launch_points<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_LINEAR: return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_QUADRATIC: return launch_points_split<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_CUBIC: return launch_points_split<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            default: return launch_points_split<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
         }
     }
     switch (kind) {
@@ -245,6 +297,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     std::vector<int> entry_of((size_t)N * std::max(desc->n_fam, 1), -1);
     std::vector<Entry> entries;
     std::vector<TermHdr> hdr((size_t)T);
+    std::vector<TermRec> rec((size_t)T);
     std::vector<TermDim> tdim;
     int B = 0;
     int64_t corners = 0;
@@ -285,6 +338,19 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         }
         h.ncorner = (int)ncorner;
         hdr[t] = h;
+        TermRec& r = rec[t];
+        std::memset(&r, 0, sizeof r);
+        r.coeff = desc->coeffs[t];
+        r.val_off = h.val_off;
+        r.info = h.k & 0xff;
+        bool packable = h.k <= 4 && (h.k == 0 || tdim[h.dim_off + h.k - 1].stride == 1);
+        for (int j = 0; j < h.k && packable; ++j) {
+            const TermDim& d = tdim[h.dim_off + j];
+            if (d.ent > 0xffff || d.stride > 0xffff) { packable = false; break; }
+            r.ent[j] = (unsigned short)d.ent;
+            r.stride[j] = (unsigned short)d.stride;
+        }
+        if (packable) r.info |= sgm::TERMREC_PACKED;
         corners += ncorner;
         kmax = std::max(kmax, h.k);
     }
@@ -316,6 +382,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     int rc = SGM_OK;
     const unsigned* cflags = nullptr;
     if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
+        (rc = upload(plan, rec, &d.rec)) ||
         (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
         (rc = upload(plan, maps, &d.maps)) || (rc = upload(plan, knots, &d.knots)) ||
         (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, flags, &cflags))) {

@@ -23,9 +23,20 @@
 
 namespace sgm {
 
-struct TermHdr { int k; int dim_off; int val_off; int ncorner; };   // 16 B, one per term
-struct TermDim { int boff; int stride; int radix; int ent; };       // 16 B, one per active dir
-struct Entry   { int dim; int knot_off; int n; int boff; };         // one per (direction, knots)
+struct __align__(16) TermHdr { int k; int dim_off; int val_off; int ncorner; };  // one per term
+struct __align__(16) TermDim { int boff; int stride; int radix; int ent; };      // one per active dir
+struct __align__(16) Entry   { int dim; int knot_off; int n; int boff; };        // (direction, knots)
+// Packed 32-byte term record of the split kernel: everything a term with <= 4 active
+// directions needs, in two 16-byte uniform loads.  `info` = k | PACKED_FLAG when the
+// entry ids and strides fit in 16 bits; otherwise the term goes through hdr/tdim.
+struct __align__(16) TermRec {
+    double coeff;
+    int val_off;
+    int info;
+    unsigned short ent[4];
+    unsigned short stride[4];
+};
+constexpr int TERMREC_PACKED = 0x100;
 
 // Device view of a plan (passed by value to the kernels).
 struct PlanDev {
@@ -34,6 +45,7 @@ struct PlanDev {
     int n_knots;                       // doubles in `knots` (and `lambda`)
     const TermHdr* hdr;
     const TermDim* tdim;
+    const TermRec* rec;
     const double* coeff;
     const Entry* ent;
     const int* maps;
@@ -242,6 +254,135 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
         double* o = out + p * ldo;
         if (accumulate) *o = *o + scale * acc;
         else *o = (scale == 1.0) ? acc : scale * acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A2 ("split"): scalar output, one block = 32 points x W warps.  The 32 lanes of every
+// warp are the 32 points of the tile; the W warps split the TERMS of a chunk among them, so
+// the per-point basis table is stored once per tile (not once per thread) and 16+ warps per
+// SM hide the gather latency.  Bit-exactness is kept by separating the two roles of the
+// reference's loop body  out = out + c_t * tp_t :
+//   (1) p_t = c_t * tp_t is computed by any warp, in any order, and parked in shared memory;
+//   (2) out = out + p_t is then applied in term order by ONE warp per chunk (rotating).
+// ---------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ double linear_term_packed(const int4 r1, const double* bas,
+                                                     const unsigned short* idx,
+                                                     const double* __restrict__ Gt) {
+    // r1 = {ent0|ent1<<16, ent2|ent3<<16, stride0|stride1<<16, stride2|stride3<<16};
+    // the last active direction always has stride 1 (C order).
+    double wl[K], wh[K];
+    unsigned st[K];
+    unsigned base = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const unsigned e = (unsigned)((j < 2 ? r1.x : r1.y) >> (16 * (j & 1))) & 0xffffu;
+        const unsigned sd = (unsigned)((j < 2 ? r1.z : r1.w) >> (16 * (j & 1))) & 0xffffu;
+        const double y = bas[e * 32];
+        wh[j] = y;
+        wl[j] = 1.0 - y;
+        st[j] = sd;
+        base += (unsigned)idx[e * 32] * sd;
+    }
+    const double* gp = Gt + base;
+    double tp = 0.0;
+#pragma unroll
+    for (int c = 0; c < (1 << K); c += 2) {
+        double w = 1.0;
+        unsigned off = 0;
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) {
+            const int bit = (c >> (K - 1 - j)) & 1;
+            w = w * (bit ? wh[j] : wl[j]);
+            off += bit ? st[j] : 0u;
+        }
+        const double* q = gp + off;
+        tp = tp + q[0] * (w * wl[K - 1]);
+        tp = tp + q[1] * (w * wh[K - 1]);
+    }
+    return tp;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(512)
+eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                         const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
+                         double scale, int accumulate, int chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+    }
+    double* bas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* sP = bas_all + (size_t)pl.B * 32;                 // [2][chunk][32]
+    double* sOut = sP + 2 * (size_t)chunk * 32;               // [32]
+    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sOut + 32);
+    const double* bas = bas_all + lane;
+    const unsigned short* idx = idx_all + lane;
+    const int4* rec4 = reinterpret_cast<const int4*>(pl.rec);
+
+    const int64_t n_tiles = (P + 31) >> 5;
+    unsigned gc = 0;                                           // chunk counter (block-uniform)
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p = (tile << 5) + lane;
+        const bool valid = p < P;
+        const double* xp = x + (valid ? p : P - 1) * ldx;
+        __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
+        for (int e = warp; e < pl.E; e += W) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
+                                             idx_all + lane, e, 32, pl.flags);
+        }
+        __syncthreads();
+        if (pl.T == 0 && warp == 0 && valid) {
+            double* o = out + p * ldo;
+            *o = accumulate ? *o + scale * 0.0 : scale * 0.0;
+        }
+        for (int t0 = 0; t0 < pl.T; t0 += chunk, ++gc) {
+            double* sp = sP + (size_t)(gc & 1u) * chunk * 32 + lane;
+            const int nt = min(chunk, pl.T - t0);
+            for (int tl = warp; tl < nt; tl += W) {
+                const int t = t0 + tl;
+                const int4 r0 = __ldg(rec4 + 2 * t);            // coeff (x,y), val_off, info
+                const double coef = __hiloint2double(r0.y, r0.x);
+                double tp;
+                if (KIND == SGM_PW_LINEAR && (r0.w & TERMREC_PACKED)) {
+                    const int4 r1 = __ldg(rec4 + 2 * t + 1);
+                    switch (r0.w & 0xff) {
+                        case 0: tp = G[r0.z]; break;
+                        case 1: tp = linear_term_packed<1>(r1, bas, idx, G + r0.z); break;
+                        case 2: tp = linear_term_packed<2>(r1, bas, idx, G + r0.z); break;
+                        case 3: tp = linear_term_packed<3>(r1, bas, idx, G + r0.z); break;
+                        default: tp = linear_term_packed<4>(r1, bas, idx, G + r0.z); break;
+                    }
+                } else {
+                    const TermHdr h = pl.hdr[t];
+                    tp = h.k == 0 ? G[h.val_off]
+                                  : generic_term<KIND>(h, pl.tdim + h.dim_off, bas, idx, 32,
+                                                       G + h.val_off);
+                }
+                sp[tl * 32] = coef * tp;
+            }
+            __syncthreads();
+            if (warp == (int)(gc % (unsigned)W)) {
+                double o = (t0 == 0) ? 0.0 : sOut[lane];
+                for (int tl = 0; tl < nt; ++tl) o = o + sp[tl * 32];
+                if (t0 + chunk >= pl.T) {
+                    if (valid) {
+                        double* dst = out + p * ldo;
+                        *dst = accumulate ? *dst + scale * o : scale * o;
+                    }
+                } else {
+                    sOut[lane] = o;
+                }
+            }
+        }
     }
 }
 

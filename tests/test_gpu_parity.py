@@ -178,7 +178,7 @@ def test_torch_tensors_in_torch_tensor_out_and_extra_columns():
     assert out.is_cuda and out.shape == (32,)
     assert rel_err(out.cpu().numpy(), g["out"]) <= TOL
     with pytest.raises(IndexError):
-        it.interpolate(g["x"][:, :5], g["f_on_SG"])            # too few columns
+        it.interpolate(g["x"][:, :1], g["f_on_SG"])            # too few columns
 
 
 def test_quadratic_right_of_last_knot_raises_index_error():
@@ -202,7 +202,8 @@ def test_cubic_with_three_knots_raises_like_reference():
 
 
 def test_lagrange_on_a_knot_is_nan_like_reference():
-    it = SGInterpolant(mis.smolyak_mid_set(2, 2), nodes_1d.hermite_nodes, lambda n: 2 * n + 1,
+    knots = lambda n: np.atleast_1d(np.asarray(nodes_1d.equispaced_nodes(n), dtype=float))  # noqa
+    it = SGInterpolant(mis.smolyak_mid_set(2, 2), knots, lambda n: 2 * n + 1,
                        tp_interpolant=TPLagrangeInterpolator, verbose=False)
     out = it.interpolate(np.array([[0.0, 0.3], [0.1, 0.3]]), np.ones((it.num_nodes, 1)))
     assert np.isnan(out[0]) and abs(out[1] - 1.0) < 1e-12
