@@ -308,6 +308,26 @@ def main():
     e2e_value = world * P * NF * e2e_steps / (float(e2e_ms.item()) * 1e-3)
     assert torch.equal(out_host.to(dev), out), "e2e result differs from the device-resident run"
 
+    gather_ms = None
+    if world > 1:
+        # the optional final exchange of the point-sharded result (north star item 4): NCCL
+        # all-gather of the (P, NF) slabs, timed separately from the collective-free step
+        from sgmethods_b200.distributed import ShardedInterpolant
+        sh = ShardedInterpolant(it, mode="points")
+        sh.gather_blocks(out, world * P, "all")
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            full = sh.gather_blocks(out, world * P, "all")
+        g1.record()
+        torch.cuda.synchronize()
+        gm = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+        assert full.shape == (world * P, NF)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         kernel_ms = float(np.mean(step_ms))
@@ -338,6 +358,10 @@ def main():
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,
         }
+        if gather_ms is not None:
+            line["final_all_gather"] = {"ms": gather_ms, "bytes_per_rank": int(P * NF * 8),
+                                        "backend": "nccl all_gather_into_tensor",
+                                        "in_timed_step": False}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or cores * 1024

@@ -258,3 +258,85 @@ def test_karhunen_loeve_against_reference_outputs():
     g = load_golden("brownian")
     W = param_KL_Brownian_motion(g["kl_tt"], g["kl_yy"])
     assert rel_err(W, g["kl_W"]) <= TOL
+
+
+# ------------------------------------------------------------------ composite drivers (a12, a14)
+def _ml_setup(kind_cls, NF, knots=None):
+    rng = np.random.default_rng(7)
+    knots = knots or nodes_1d.cc_nodes
+    lev = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa: E731
+    seq = [SGInterpolant(mis.smolyak_mid_set(k, 4), knots, lev, tp_interpolant=kind_cls,
+                         verbose=False) for k in range(4)]
+    K = len(seq) - 1
+    ml = [rng.normal(size=(seq[K - k].num_nodes, NF)) for k in range(K + 1)]
+    yy = rng.uniform(-1, 1, (400, 4))
+    return seq, ml, yy
+
+
+@pytest.mark.parametrize("kind,NF", [("linear", 1), ("quadratic", 24), ("linear", 70)])
+def test_multilevel_interpolant_against_oracle(kind, NF):
+    from oracle import drivers_oracle
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant, MultilevelInterpolant
+    assert MultilevelInterpolant is MLInterpolant
+    seq, ml, yy = _ml_setup(KIND_CLASS[kind], NF)
+    mli = MLInterpolant(seq)
+    plans = [oracle_plan_of(it) for it in seq]
+    for p, it in zip(plans, seq):
+        p.SG = it.SG
+    ref = drivers_oracle.ml_interpolate(plans, kind, yy, ml)
+    got = mli.interpolate(yy, ml)
+    assert rel_err(got, ref) <= TOL
+    ref_terms = drivers_oracle.ml_terms(plans, kind, yy, ml)
+    got_terms = mli.get_ml_terms(yy, ml)
+    assert len(got_terms) == 4
+    for a, b in zip(got_terms, ref_terms):
+        assert rel_err(a, b) <= TOL
+    assert mli.total_cost(np.array([1., 10., 100., 1000.])) == \
+        sum(seq[k].num_nodes * [1., 10., 100., 1000.][3 - k] for k in range(4))
+
+
+def test_multilevel_sample_and_non_nested_grids():
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    seq, _, yy = _ml_setup(TPPwLinearInterpolator, 1)
+    mli = MLInterpolant(seq)
+    ml = mli.sample(lambda y, k: np.array([np.sin(np.sum(y)) + 2.0 ** (-k), float(k)]))
+    assert [s.shape for s in ml] == [(seq[3 - k].num_nodes, 2) for k in range(4)]
+    assert np.all(ml[2][:, 1] == 2.0)
+    val = mli.interpolate(yy, ml)
+    assert val.shape == (400, 2) and np.all(np.isfinite(val))
+    lev = lambda n: n + 1  # noqa: E731   (cc_nodes with n+1 knots: not nested)
+    bad = [SGInterpolant(mis.smolyak_mid_set(k, 2), nodes_1d.cc_nodes, lev, verbose=False)
+           for k in (2, 3)]
+    with pytest.raises(ZeroDivisionError):
+        MLInterpolant(bad).interpolate(yy[:, :2], [np.ones((bad[1].num_nodes, 1)),
+                                                   np.ones((bad[0].num_nodes, 1))])
+
+
+def test_error_indicators_against_oracle():
+    from oracle import drivers_oracle
+    from sgmethods_b200.compute_error_indicators import compute_GG_indicators_RM
+    from sgmethods_b200.mid_set import MidSet
+    ms = MidSet(track_reduced_margin=True)
+    for op, arg in (("e", 0), ("d", None), ("e", 1), ("e", 0), ("d", None), ("e", 2)):
+        ms.enlarge_from_margin(arg) if op == "e" else ms.increase_dim()
+    knots = nodes_1d.unbounded_nodes_nested
+    lev = lambda n: 2 ** (n + 1) - 1  # noqa: E731
+    f = lambda y: np.array([np.exp(-0.3 * np.sum(y * y)), np.sum(y)])  # noqa: E731
+    norm = lambda a, b: float(np.sqrt(np.mean(np.sum((a - b) ** 2, axis=1))))  # noqa: E731
+    cur = SGInterpolant(ms.mid_set, knots, lev, verbose=False)
+    u_on_SG = cur.sample_on_SG(f)
+    yy = np.random.default_rng(3).normal(size=(500, ms.get_dim()))
+    u_interp = cur.interpolate(yy, u_on_SG)
+    got = compute_GG_indicators_RM(np.zeros((0, 0), dtype=int), np.zeros(0), ms, knots, lev, f,
+                                   cur.SG, u_on_SG, yy, norm, u_interp)
+    ref = drivers_oracle.gg_indicators(ms.mid_set, ms.reduced_margin, knots, lev, f, cur.SG,
+                                       u_on_SG, yy, norm, u_interp)
+    assert got.shape == (ms.get_cardinality_reduced_margin(),)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    assert np.all(got > 0)
+    # recycling: unchanged reduced-margin entries are copied, not recomputed
+    calls = []
+    again = compute_GG_indicators_RM(ms.reduced_margin[:-1], got[:-1] + 1.0, ms, knots, lev,
+                                     lambda y: (calls.append(1), f(y))[1], cur.SG, u_on_SG, yy,
+                                     norm, u_interp)
+    assert np.array_equal(again[:-1], got[:-1] + 1.0) and abs(again[-1] - got[-1]) < 1e-14
