@@ -74,11 +74,11 @@ def param_KL_Brownian_motion(tt, yy):
     P, nt = y_d.shape[0], t_d.numel()
     W = torch.empty((P, nt), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    factor_d = torch.from_numpy(factor).to(dev)      # keep alive until the launch is queued
+    freq_d = torch.from_numpy(freq).to(dev)
     _lib.check(_lib.load().sgm_kl_brownian(
         t_d.data_ptr(), nt, y_d.data_ptr(), P, d, y_d.stride(0) if P > 1 else max(d, 1),
-        torch.from_numpy(factor).to(dev).data_ptr(), torch.from_numpy(freq).to(dev).data_ptr(),
-        W.data_ptr(), max(nt, 1), stream))
-    torch.cuda.current_stream(dev).synchronize()
+        factor_d.data_ptr(), freq_d.data_ptr(), W.data_ptr(), max(nt, 1), stream))
     if single:
         W = W.reshape(-1)
     return W if as_torch else W.cpu().numpy()

@@ -304,9 +304,9 @@ def test_multilevel_sample_and_non_nested_grids():
     assert np.all(ml[2][:, 1] == 2.0)
     val = mli.interpolate(yy, ml)
     assert val.shape == (400, 2) and np.all(np.isfinite(val))
-    lev = lambda n: n + 1  # noqa: E731   (cc_nodes with n+1 knots: not nested)
-    bad = [SGInterpolant(mis.smolyak_mid_set(k, 2), nodes_1d.cc_nodes, lev, verbose=False)
-           for k in (2, 3)]
+    lev = lambda n: n + 1  # noqa: E731   (n+1 knots: the two families below do not nest)
+    bad = [SGInterpolant(mis.smolyak_mid_set(k, 2), fam, lev, verbose=False)
+           for k, fam in ((2, nodes_1d.equispaced_interior_nodes), (3, nodes_1d.cc_nodes))]
     with pytest.raises(ZeroDivisionError):
         MLInterpolant(bad).interpolate(yy[:, :2], [np.ones((bad[1].num_nodes, 1)),
                                                    np.ones((bad[0].num_nodes, 1))])
