@@ -117,6 +117,17 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
 // Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
 struct SplitLaunch { int warps; int chunk; size_t smem; int blocks_per_sm; };
 
+using SplitKernel = void (*)(const PlanDev, const double*, int64_t, int64_t, const double*,
+                             double*, int64_t, double, int);
+
+template <int KIND>
+SplitKernel split_kernel_for(int warps, int chunk) {
+    if (warps == 16 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 16, 64>;
+    if (warps == 8 && chunk == 32) return sgm::eval_points_split_kernel<KIND, 8, 32>;
+    if (warps == 8 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 8, 64>;
+    return sgm::eval_points_split_kernel<KIND, 4, 32>;
+}
+
 template <int KIND>
 SplitLaunch choose_split_launch(const sgm_plan* plan) {
     const PlanDev& d = plan->dev;
@@ -128,7 +139,7 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
     for (const auto& c : cand) {
         const size_t smem = fixed + 2 * (size_t)c[1] * 32 * 8;
         if (smem > (size_t)plan->max_smem_optin) continue;
-        auto kern = sgm::eval_points_split_kernel<KIND>;
+        SplitKernel kern = split_kernel_for<KIND>(c[0], c[1]);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             continue;
         int bps = 0;
@@ -157,10 +168,10 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
     const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
-    auto kern = sgm::eval_points_split_kernel<KIND>;
+    SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk);
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
-                                                            scale, accumulate, L.chunk);
+                                                            scale, accumulate);
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }

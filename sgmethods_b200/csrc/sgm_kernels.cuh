@@ -304,15 +304,16 @@ __device__ __forceinline__ double linear_term_packed(const int4 r1, const double
     return tp;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(512)
+template <int KIND, int W, int CHUNK>
+__global__ void __launch_bounds__(W * 32)
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
-                         double scale, int accumulate, int chunk) {
+                         double scale, int accumulate) {
+    constexpr int chunk = CHUNK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int W = blockDim.x >> 5;
+    static_assert((W & (W - 1)) == 0, "W must be a power of two");
     double* sknots = reinterpret_cast<double*>(smem_raw);
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
@@ -370,7 +371,7 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                 sp[tl * 32] = coef * tp;
             }
             __syncthreads();
-            if (warp == (int)(gc % (unsigned)W)) {
+            if (warp == (int)(gc & (unsigned)(W - 1))) {
                 double o = (t0 == 0) ? 0.0 : sOut[lane];
                 for (int tl = 0; tl < nt; ++tl) o = o + sp[tl * 32];
                 if (t0 + chunk >= pl.T) {

@@ -40,3 +40,6 @@ for d in range(16):
 perm = torch.argsort(key)
 o2 = timeit(x[perm].contiguous(), "sorted by 7-knot cell of all dims (lexicographic)")
 assert torch.equal(o2, o0[perm])
+# floor without gather divergence: all points identical -> every gather is a broadcast
+xsame = x[:1].expand(P, -1).contiguous()
+timeit(xsame, "all points identical (broadcast gathers: issue/FP64/smem floor)")
