@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -163,7 +164,10 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                         double* out, int64_t ldo, double scale, int accumulate,
                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const SplitLaunch L = choose_split_launch<KIND>(plan);
-    if (L.warps == 0 || L.blocks_per_sm * L.warps < 8)      // tables too large: thread-per-point
+    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split"
+    const bool want_v1 = force ? std::strcmp(force, "v1") == 0
+                               : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
+    if (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8)   // few terms / huge tables
         return launch_points<KIND>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
@@ -472,10 +476,26 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
     int dev = 0, sms = 148;
     SGM_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t total = P * nt;
-    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
-    sgm::lc_brownian_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (L <= 12 && nt >= 32) {
+        const int tpt = L <= 6 ? 4 : 2;
+        const int64_t gx = (nt + 256 * tpt - 1) / (256 * tpt);
+        // enough blocks to fill the GPU several times over, at least 8 rows per block
+        int64_t rows = std::max<int64_t>(8, (P * gx + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16));
+        int64_t gy = (P + rows - 1) / rows;
+        if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
+        if (L <= 6)
+            sgm::lc_brownian_tiles_kernel<6, 4><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(
+                tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
+        else
+            sgm::lc_brownian_tiles_kernel<12, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(
+                tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
+    } else {
+        const int64_t total = P * nt;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+        sgm::lc_brownian_kernel<<<blocks, 256, 0, st>>>(tt, nt, yy, P, d, ldy, T, sqrtT,
+                                                        level_scale, L, W, ldw);
+    }
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }

@@ -462,13 +462,29 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
                     int row = 0;
                     if (cid < h.ncorner) {
                         int off = 0;
-                        int cs = h.ncorner;
-                        for (int j = 0; j < h.k; ++j) {
-                            const TermDim d = td[j];
-                            cs /= d.radix;
-                            const int a = (cid / cs) % d.radix;
-                            w = w * digit_weight<KIND>(bas, 1, d, a);
-                            off += (idx[d.ent] + a) * d.stride;
+                        if (KIND == SGM_LAGRANGE) {
+                            int cs = h.ncorner;
+                            for (int j = 0; j < h.k; ++j) {
+                                const TermDim d = td[j];
+                                cs /= d.radix;
+                                const int a = (cid / cs) % d.radix;
+                                w = w * digit_weight<KIND>(bas, 1, d, a);
+                                off += (idx[d.ent] + a) * d.stride;
+                            }
+                        } else {
+                            // fixed radix 2 / 3 / 4: digits by constant division, most
+                            // significant digit = first active direction
+                            constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
+                            int cs = h.ncorner;
+                            int rem = cid;
+                            for (int j = 0; j < h.k; ++j) {
+                                const TermDim d = td[j];
+                                cs /= R;
+                                const int a = rem / cs;
+                                rem -= a * cs;
+                                w = w * digit_weight<KIND>(bas, 1, d, a);
+                                off += (idx[d.ent] + a) * d.stride;
+                            }
                         }
                         row = tmap[off];
                     }
@@ -480,7 +496,7 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) {
                             const int64_t col = col0 + 32 * c;
-                            if (col < NF) tp[c] = tp[c] + fr[col] * wv;
+                            if (col < NF) tp[c] = tp[c] + __ldg(fr + col) * wv;
                         }
                     }
                 }
@@ -533,6 +549,72 @@ __global__ void lc_brownian_kernel(const double* __restrict__ tt, int64_t nt,
             }
         }
         W[p * ldw + it] = w * sqrtT;
+    }
+}
+
+// Fast path (L <= LMAX): a block owns a chunk of 256*TPT consecutive times and a range of
+// rows.  Each thread computes the per-level hat index and hat value of its TPT times ONCE
+// (they do not depend on the parameter vector) and then streams over the rows: per output
+// L x (load y_k, two multiplies, one add) and one store; a block writes 2*TPT KB of every row
+// contiguously, which keeps the HBM write stream page-friendly.
+template <int LMAX, int TPT>
+__global__ void __launch_bounds__(256)
+lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
+                         const double* __restrict__ yy, int64_t P, int d, int64_t ldy, double T,
+                         double sqrtT, const double* __restrict__ level_scale, int L,
+                         double* __restrict__ W, int64_t ldw, int rows_per_block) {
+    const int64_t t_base = (int64_t)blockIdx.x * (256 * TPT) + threadIdx.x;
+    int kidx[TPT][LMAX];
+    double eta[TPT][LMAX], sv[TPT], scl[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) scl[l] = l < L ? level_scale[l] : 0.0;
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+        const int64_t it = t_base + q * 256;
+        const double s = it < nt ? tt[it] / T : 0.0;
+        sv[q] = s;
+        const bool inside = (s >= 0.0 && s <= 1.0);
+#pragma unroll
+        for (int l = 1; l <= LMAX; ++l) {
+            // inactive levels (outside [0,1], zero padding) read y[0] with eta = 0: they add
+            // an exact zero, which is also what the reference's sum over all hats does
+            kidx[q][l - 1] = 0;
+            eta[q][l - 1] = 0.0;
+            if (l <= L && inside) {
+                const int64_t half = (int64_t)1 << (l - 1);
+                const double inv = 1.0 / (double)(half << 1);
+                int64_t j = (int64_t)floor(s * (double)half);
+                if (j > half - 1) j = half - 1;
+                const int64_t k = half + j;
+                if (k < d) {
+                    const double left = (double)(2 * j) * inv;
+                    const double mid = (double)(2 * j + 1) * inv;
+                    const double right = (double)(2 * j + 2) * inv;
+                    kidx[q][l - 1] = (int)k;
+                    eta[q][l - 1] = (s >= mid) ? (-s + right) : (s - left);
+                }
+            }
+        }
+    }
+    const int64_t p0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t p1 = min(P, p0 + rows_per_block);
+    for (int64_t p = p0; p < p1; ++p) {
+        const double* y = yy + p * ldy;
+        const double y0 = __ldg(y);
+        double* wrow = W + p * ldw;
+        double yk[TPT][LMAX];
+#pragma unroll
+        for (int q = 0; q < TPT; ++q)
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) yk[q][l] = __ldg(y + kidx[q][l]);
+#pragma unroll
+        for (int q = 0; q < TPT; ++q) {
+            double w = y0 * sv[q];
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) w = w + (yk[q][l] * scl[l]) * eta[q][l];
+            const int64_t it = t_base + q * 256;
+            if (it < nt) wrow[it] = w * sqrtT;
+        }
     }
 }
 

@@ -42,23 +42,42 @@ def _prep(tt, yy):
     return torch, as_torch, dev, t_d.reshape(-1), y_d, single
 
 
+_SCALE_CACHE = {}
+
+
+def lc_brownian_device(t_d, y_d, T, out=None):
+    """Launch-only form: ``t_d`` (nt,) and ``y_d`` (P, d) are fp64 CUDA tensors; returns the
+    (P, nt) CUDA tensor of expansions.  No host synchronisation, no range check."""
+    from ._device import torch_cuda
+    torch = torch_cuda()
+    dev = y_d.device
+    d = y_d.shape[1]
+    L = ceil(log(d, 2))
+    key = (L, dev.index)
+    if key not in _SCALE_CACHE:        # 2^((l-1)/2) as the reference computes it (python floats)
+        scale = np.array([2 ** ((lev - 1) / 2) for lev in range(1, L + 1)] or [0.0])
+        _SCALE_CACHE[key] = torch.from_numpy(scale).to(dev)
+    P, nt = y_d.shape[0], t_d.numel()
+    W = out if out is not None else torch.empty((P, nt), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.load().sgm_lc_brownian(
+        t_d.data_ptr(), nt, y_d.data_ptr(), P, d, y_d.stride(0) if P > 1 else d, float(T),
+        float(np.sqrt(T)), _SCALE_CACHE[key].data_ptr(), L, W.data_ptr(),
+        W.stride(0) if P > 1 else max(nt, 1), stream))
+    return W
+
+
 def param_LC_Brownian_motion(tt, yy, T):
     """Levy-Ciesielski expansion W(y, t) = sqrt(T) [ y_0 s + sum_{l,j} y_{l,j} 2^((l-1)/2)
     eta_{l,j}(s) ], s = t/T, with the Faber-Schauder hats eta_{l,j} on [0, 1]; the number of
     levels is ceil(log2 d) and the last level may be incomplete (zero padding)."""
     torch, as_torch, dev, t_d, y_d, single = _prep(tt, yy)
-    if t_d.numel() and (bool(t_d.max() > T) or bool(t_d.min() < 0)):
-        warnings.warn("Warning...........tt not within [0,T]")
-    d = y_d.shape[1]
-    L = ceil(log(d, 2))
-    scale = np.array([2 ** ((lev - 1) / 2) for lev in range(1, L + 1)], dtype=np.float64)
-    scale_d = torch.from_numpy(scale).to(dev) if L else torch.zeros(1, dtype=torch.float64, device=dev)
-    P, nt = y_d.shape[0], t_d.numel()
-    W = torch.empty((P, nt), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.load().sgm_lc_brownian(
-        t_d.data_ptr(), nt, y_d.data_ptr(), P, d, y_d.stride(0) if P > 1 else d, float(T),
-        float(np.sqrt(T)), scale_d.data_ptr(), L, W.data_ptr(), max(nt, 1), stream))
+    if t_d.numel():
+        lo, hi = (np.amin(tt), np.amax(tt)) if isinstance(tt, np.ndarray) else \
+            (float(v) for v in torch.aminmax(t_d))
+        if hi > T or lo < 0:
+            warnings.warn("Warning...........tt not within [0,T]")
+    W = lc_brownian_device(t_d, y_d, T)
     if single:
         W = W.reshape(-1)
     return W if as_torch else W.cpu().numpy()
