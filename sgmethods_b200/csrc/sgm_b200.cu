@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -115,11 +116,17 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
     return best;
 }
 
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int64_t kSortMinPoints = 32768;
+size_t sort_scratch_bytes(int64_t P) {
+    return align_up((size_t)P * 4, 256) + 65536 * 4 + align_up((size_t)P * 2, 256);
+}
+
 // Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
 struct SplitLaunch { int warps; int chunk; size_t smem; int blocks_per_sm; };
 
 using SplitKernel = void (*)(const PlanDev, const double*, int64_t, int64_t, const double*,
-                             double*, int64_t, double, int);
+                             double*, int64_t, double, int, const int*);
 
 template <int KIND>
 SplitKernel split_kernel_for(int warps, int chunk) {
@@ -172,10 +179,29 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
     const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+    // locality sort of the points (scratch: perm P ints | keys P u16 | 65536 bins)
+    const int* perm = nullptr;
+    const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
+    if (P >= kSortMinPoints && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort) {
+        const size_t need = sort_scratch_bytes(P);
+        if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
+        int* perm_w = reinterpret_cast<int*>(scratch);
+        unsigned* hist = reinterpret_cast<unsigned*>(scratch + align_up((size_t)P * 4, 256));
+        unsigned short* keys = reinterpret_cast<unsigned short*>(
+            scratch + align_up((size_t)P * 4, 256) + 65536 * 4);
+        const int nbins = 1 << plan->dev.n_key;
+        SGM_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, stream));
+        const int sblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)plan->sm_count * 8);
+        sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys);
+        sgm::sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, nbins);
+        sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, perm_w);
+        SGM_CUDA(cudaGetLastError());
+        perm = perm_w;
+    }
     SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk);
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
-                                                            scale, accumulate);
+                                                            scale, accumulate, perm);
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }
@@ -239,7 +265,6 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
     return launch_cols_cpl<KIND, 4>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
 }
 
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t M,
              int64_t NF, int64_t ldf, double* out, int64_t ldo, double scale, int accumulate,
@@ -388,6 +413,26 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     d.kind = kind; d.N = N; d.E = (int)entries.size(); d.B = B; d.T = (int)T;
     d.n_knots = (int)n_knots;
 
+    {   // locality key: the (up to 16) most used directions, threshold = middle knot of the
+        // smallest knot family with an interior knot used in that direction
+        std::vector<int64_t> usage(N, 0);
+        std::vector<int> small_fam(N, -1);
+        for (const TermDim& td : tdim) {
+            const Entry& e = entries[td.ent];
+            ++usage[e.dim];
+            if (e.n >= 3 && (small_fam[e.dim] < 0 || e.n < entries[small_fam[e.dim]].n))
+                small_fam[e.dim] = td.ent;
+        }
+        std::vector<int> order;
+        for (int n = 0; n < N; ++n) if (small_fam[n] >= 0) order.push_back(n);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return usage[a] > usage[b]; });
+        d.n_key = (int)std::min<size_t>(order.size(), 16);
+        for (int i = 0; i < d.n_key; ++i) {
+            const Entry& e = entries[small_fam[order[i]]];
+            d.key_dim[i] = e.dim;
+            d.key_thr[i] = desc->fam_knots[e.knot_off + e.n / 2];
+        }
+    }
     std::vector<double> coeff(desc->coeffs, desc->coeffs + T);
     std::vector<int> maps(desc->maps, desc->maps + desc->map_off[T]);
     std::vector<double> knots(desc->fam_knots, desc->fam_knots + n_knots);
@@ -435,13 +480,15 @@ size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
     if (!plan || NF != 1) return 256;
     size_t bytes = align_up((size_t)plan->n_vals * 8, 256);
     const PointLaunch L = choose_point_launch(plan);
+    size_t scratch = 0;
     if (L.global_basis) {
         const int64_t tiles = (P + L.threads - 1) / std::max(L.threads, 1);
         const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
-        bytes += (size_t)std::max<int64_t>(blocks, 1) * L.threads *
-                 ((size_t)plan->dev.B * 8 + (size_t)plan->dev.E * 2);
+        scratch = (size_t)std::max<int64_t>(blocks, 1) * L.threads *
+                  ((size_t)plan->dev.B * 8 + (size_t)plan->dev.E * 2);
     }
-    return bytes + 256;
+    if (P >= kSortMinPoints) scratch = std::max(scratch, sort_scratch_bytes(P));
+    return bytes + scratch + 256;
 }
 
 int sgm_eval(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t M,

@@ -52,6 +52,11 @@ struct PlanDev {
     const double* knots;
     const double* lambda;
     unsigned* flags;
+    // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
+    // coarsest knot family used in that direction), for the n_key most used directions
+    int n_key;
+    int key_dim[16];
+    double key_thr[16];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -308,7 +313,7 @@ template <int KIND, int W, int CHUNK>
 __global__ void __launch_bounds__(W * 32)
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
-                         double scale, int accumulate) {
+                         double scale, int accumulate, const int* __restrict__ perm) {
     constexpr int chunk = CHUNK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -331,9 +336,12 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
     const int64_t n_tiles = (P + 31) >> 5;
     unsigned gc = 0;                                           // chunk counter (block-uniform)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t p = (tile << 5) + lane;
-        const bool valid = p < P;
-        const double* xp = x + (valid ? p : P - 1) * ldx;
+        // lanes of a tile = 32 consecutive points, or 32 consecutive entries of the locality
+        // permutation (points whose coarse brackets agree gather from the same cache lines)
+        const int64_t slot = (tile << 5) + lane;
+        const bool valid = slot < P;
+        const int64_t p = perm ? (int64_t)perm[valid ? slot : P - 1] : (valid ? slot : P - 1);
+        const double* xp = x + p * ldx;
         __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
         for (int e = warp; e < pl.E; e += W) {
             const Entry en = pl.ent[e];
@@ -385,6 +393,55 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Locality sort of the evaluation points (counting sort on a <= 16-bit key).  Each point is
+// evaluated independently, so the order only changes which points share a warp: with equal
+// coarse brackets the 32 lanes of a gather hit 1-2 cache lines instead of 4-5.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned locality_key(const PlanDev& pl, const double* xp) {
+    unsigned key = 0;
+    for (int i = 0; i < pl.n_key; ++i) key |= (xp[pl.key_dim[i]] >= pl.key_thr[i] ? 1u : 0u) << i;
+    return key;
+}
+__global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
+                                 int64_t ldx, unsigned* __restrict__ hist,
+                                 unsigned short* __restrict__ keys) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned key = locality_key(pl, x + p * ldx);
+        keys[p] = (unsigned short)key;
+        atomicAdd(hist + key, 1u);
+    }
+}
+// exclusive scan of `n` (<= 65536) bins by one block of 1024 threads
+__global__ void sort_scan_kernel(unsigned* __restrict__ hist, int n) {
+    __shared__ unsigned part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    unsigned sum = 0;
+    for (int i = lo; i < hi; ++i) sum += hist[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+__global__ void sort_scatter_kernel(const unsigned short* __restrict__ keys, int64_t P,
+                                    unsigned* __restrict__ offs, int* __restrict__ perm) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
+         p += (int64_t)gridDim.x * blockDim.x)
+        perm[atomicAdd(offs + keys[p], 1u)] = (int)p;
 }
 
 // G[j, 0:NF] = f[maps[j], 0:NF]  (the reference's per-term fancy-index copy,
