@@ -196,6 +196,50 @@ __device__ __noinline__ double generic_term(const TermHdr h, const TermDim* __re
     return tp;
 }
 
+// Nested-loop walk of ALL corner / node contributions of a term with K active directions
+// (K compile-time, trip counts run-time): the weight prefix ((1*b_0)*b_1)*... is carried
+// down the recursion in registers, so a contribution costs one weight multiply, one value
+// multiply and one add -- in C order, i.e. the reference's order (tp_inteprolants.py:146-160,
+// :263-277, :339-360).  Used for quadratic / cubic / Lagrange and for pw-linear terms with
+// more than 4 active directions.  For Lagrange every lane reads the same node value
+// (broadcast load), for the local operators the start index differs per lane.
+template <int KIND, int J, int K>
+__device__ __forceinline__ void nested_walk(const TermDim* __restrict__ td, const double* bas,
+                                            const unsigned short* idx, int bs,
+                                            const double* __restrict__ Gt, double w, int off,
+                                            double& tp) {
+    const TermDim d = td[J];
+    const int start = (KIND == SGM_LAGRANGE) ? 0 : (int)idx[(size_t)d.ent * bs];
+    const int base = off + start * d.stride;
+    for (int a = 0; a < d.radix; ++a) {
+        const double wa = w * digit_weight<KIND>(bas, bs, d, a);
+        if constexpr (J + 1 == K) {
+            tp = tp + Gt[base + a * d.stride] * wa;
+        } else {
+            nested_walk<KIND, J + 1, K>(td, bas, idx, bs, Gt, wa, base + a * d.stride, tp);
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ double walk_term(const TermHdr h, const TermDim* __restrict__ td,
+                                            const double* bas, const unsigned short* idx, int bs,
+                                            const double* __restrict__ Gt) {
+    double tp = 0.0;
+    switch (h.k) {
+        case 1: nested_walk<KIND, 0, 1>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 2: nested_walk<KIND, 0, 2>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 3: nested_walk<KIND, 0, 3>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 4: nested_walk<KIND, 0, 4>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 5: nested_walk<KIND, 0, 5>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 6: nested_walk<KIND, 0, 6>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 7: nested_walk<KIND, 0, 7>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        case 8: nested_walk<KIND, 0, 8>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
+        default: tp = generic_term<KIND>(h, td, bas, idx, bs, Gt); break;
+    }
+    return tp;
+}
+
 template <int KIND, bool GLOBAL_BASIS>
 __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
                                    int64_t ldx, const double* __restrict__ G,
@@ -252,7 +296,7 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
                     default: tp = linear_term<4>(td, bas, idx, bs, Gt); break;
                 }
             } else {
-                tp = generic_term<KIND>(h, td, bas, idx, bs, Gt);
+                tp = walk_term<KIND>(h, td, bas, idx, bs, Gt);
             }
             acc = acc + c * tp;
         }
@@ -373,8 +417,8 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                 } else {
                     const TermHdr h = pl.hdr[t];
                     tp = h.k == 0 ? G[h.val_off]
-                                  : generic_term<KIND>(h, pl.tdim + h.dim_off, bas, idx, 32,
-                                                       G + h.val_off);
+                                  : walk_term<KIND>(h, pl.tdim + h.dim_off, bas, idx, 32,
+                                                    G + h.val_off);
                 }
                 sp[tl * 32] = coef * tp;
             }
