@@ -289,7 +289,10 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         SGM_CUDA(cudaGetLastError());
         const size_t sb = workspace_bytes - g_bytes;
         switch (kind) {
-            case SGM_PW_LINEAR: return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_LINEAR:
+                if (plan->kmax > 4)
+                    return launch_points_split<sgm::SGM_LINEAR_WIDE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+                return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             case SGM_PW_QUADRATIC: return launch_points_split<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             case SGM_PW_CUBIC: return launch_points_split<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             default: return launch_points_split<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);

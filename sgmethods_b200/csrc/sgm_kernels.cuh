@@ -37,6 +37,13 @@ struct __align__(16) TermRec {
     unsigned short stride[4];
 };
 constexpr int TERMREC_PACKED = 0x100;
+// internal kernel flavour: pw-linear plan that has terms with more than 4 active directions;
+// every term goes through the nested walk (the 4-direction fast path is compiled out so that
+// it keeps its register budget in the common flavour)
+constexpr int SGM_LINEAR_WIDE = 4;
+__host__ __device__ constexpr int base_kind(int kind) {
+    return kind == SGM_LINEAR_WIDE ? (int)SGM_PW_LINEAR : kind;
+}
 
 // Device view of a plan (passed by value to the kernels).
 struct PlanDev {
@@ -86,7 +93,7 @@ __device__ __forceinline__ void fill_basis(const Entry e, double x, const double
     const double* g = knots + e.knot_off;
     const int n = e.n;
     double* b = bas + (size_t)e.boff * bs;
-    if (KIND == SGM_PW_LINEAR) {
+    if (base_kind(KIND) == SGM_PW_LINEAR) {
         int i = count_le(g, n, x) - 1;
         i = max(0, min(i, n - 2));
         b[0] = (x - g[i]) / (g[i + 1] - g[i]);
@@ -130,7 +137,7 @@ __device__ __forceinline__ void fill_basis(const Entry e, double x, const double
 // weight of digit `a` in the direction described by `d`
 template <int KIND>
 __device__ __forceinline__ double digit_weight(const double* bas, int bs, const TermDim d, int a) {
-    if (KIND == SGM_PW_LINEAR) {
+    if (base_kind(KIND) == SGM_PW_LINEAR) {
         const double y = bas[(size_t)d.boff * bs];
         return a ? y : 1.0 - y;
     }
@@ -222,9 +229,9 @@ __device__ __forceinline__ void nested_walk(const TermDim* __restrict__ td, cons
 }
 
 template <int KIND>
-__device__ __forceinline__ double walk_term(const TermHdr h, const TermDim* __restrict__ td,
-                                            const double* bas, const unsigned short* idx, int bs,
-                                            const double* __restrict__ Gt) {
+__device__ __forceinline__ double walk_term_inl(const TermHdr h, const TermDim* __restrict__ td,
+                                                const double* bas, const unsigned short* idx,
+                                                int bs, const double* __restrict__ Gt) {
     double tp = 0.0;
     switch (h.k) {
         case 1: nested_walk<KIND, 0, 1>(td, bas, idx, bs, Gt, 1.0, 0, tp); break;
@@ -238,6 +245,16 @@ __device__ __forceinline__ double walk_term(const TermHdr h, const TermDim* __re
         default: tp = generic_term<KIND>(h, td, bas, idx, bs, Gt); break;
     }
     return tp;
+}
+// pw-linear reaches this only for terms with more than 4 active directions: it keeps the
+// simple out-of-line corner loop so that the rare path does not inflate the registers of the
+// unrolled fast path; the other kinds use the nested walk.
+template <int KIND>
+__device__ __forceinline__ double walk_term(const TermHdr h, const TermDim* __restrict__ td,
+                                            const double* bas, const unsigned short* idx, int bs,
+                                            const double* __restrict__ Gt) {
+    if constexpr (KIND == SGM_PW_LINEAR) return generic_term<KIND>(h, td, bas, idx, bs, Gt);
+    else return walk_term_inl<KIND>(h, td, bas, idx, bs, Gt);
 }
 
 template <int KIND, bool GLOBAL_BASIS>
