@@ -343,14 +343,15 @@ def main():
                        "terms": len(it._coeffs), "nodes": it.num_nodes,
                        "corners_per_point": corners, "l2": "flushed between timed steps "
                        "(256 MB fill)", "sharding": "points, no collective"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 5 * args.steps,   # pregather, sort hist/scan/scatter, eval
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
                     "d2h_bytes_per_step": int(P * NF * 8), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
-                         "kernel": "sgm::eval_points_kernel<linear> (+ pregather, <1% of the step)",
+                         "kernel": "sgm::eval_points_split_kernel<pw-linear,16,64> (+ pregather and "
+                                   "the point locality sort, ~1% of the step)",
                          "kernel_ms": kernel_ms,
                          "note": "direct combination form is bound by on-chip gathers and FP64 "
                                  "issue, not HBM (DESIGN.md): secondary figures below",

@@ -2,6 +2,7 @@
 // launch heuristics and the entry points that enqueue the kernels of sgm_kernels.cuh.
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
@@ -256,10 +257,62 @@ int launch_cols_cpl(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, con
     return SGM_OK;
 }
 
+template <int KIND, int CPL2>
+int launch_cols_wide(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                     int64_t ldf, int64_t n_tiles, double* out, int64_t ldo, double scale,
+                     int accumulate, cudaStream_t stream) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1);
+    const size_t per_warp = (size_t)d.B * 8 + (size_t)d.E * 4;
+    int warps = 8;
+    while (warps > 1 && fixed + per_warp * warps > (size_t)plan->max_smem_optin) warps >>= 1;
+    const size_t smem = fixed + per_warp * warps;
+    if (smem > (size_t)plan->max_smem_optin)
+        return sgm_fail(SGM_ERR_OVERFLOW, "per-point basis table exceeds shared memory");
+    const int pts_per_block = warps * 8;
+    const int64_t gx = (P + pts_per_block - 1) / pts_per_block;
+    if (gx > 0x7fffffff || n_tiles > 65535) return sgm_fail(SGM_ERR_OVERFLOW, "grid too large");
+    auto kern = sgm::eval_cols_wide_kernel<KIND, CPL2>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
+        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, pts_per_block);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+template <int KIND>
+int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                       int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
+                       int accumulate, cudaStream_t stream);
+
 template <int KIND>
 int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                 int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale, int accumulate,
                 cudaStream_t stream) {
+    // full 256-column (or 128-column) tiles through the wide kernel, the ragged rest through
+    // the guarded kernel; needs 16-byte aligned rows
+    const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                         (ldf % 2 == 0) && (ldo % 2 == 0);
+    const char* nowide = std::getenv("SGM_NO_WIDE");          // dev knob
+    if (aligned && !nowide && NF >= 128) {
+        const int tile = NF >= 512 ? 256 : 128;
+        const int64_t n_tiles = NF / tile;
+        int rc = tile == 256
+            ? launch_cols_wide<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
+            : launch_cols_wide<KIND, 2>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream);
+        if (rc) return rc;
+        const int64_t done = n_tiles * tile;
+        if (done == NF) return SGM_OK;
+        return launch_cols_narrow<KIND>(plan, x, P, ldx, f + done, ldf, NF - done, out + done, ldo,
+                                        scale, accumulate, stream);
+    }
+    return launch_cols_narrow<KIND>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+}
+
+template <int KIND>
+int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                       int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
+                       int accumulate, cudaStream_t stream) {
     if (NF <= 32) return launch_cols_cpl<KIND, 1>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
     if (NF <= 64) return launch_cols_cpl<KIND, 2>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
     return launch_cols_cpl<KIND, 4>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);

@@ -635,6 +635,132 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel B3 ("wide"): vector-valued output, full column tiles only.  Same structure as
+// eval_cols_kernel (one warp per point, 32 lanes compute weight + row of 32 corners, then
+// the warp walks them in order) but every lane owns CPL2 pairs of adjacent columns and
+// fetches them with 16-byte loads, without column guards: per corner 3 shuffles, one
+// address and CPL2 LDG.128 feed 4*CPL2 FP64 operations, so the FP64 pipe (not instruction
+// issue) becomes the limiter.  The ragged last columns go through eval_cols_kernel.
+// Requires 16-byte aligned rows: f, out 16-byte aligned, ldf and ldo even.
+// ---------------------------------------------------------------------------------------
+template <int KIND, int CPL2>
+__global__ void __launch_bounds__(256)
+eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                      const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                      int64_t ldo, double scale, int accumulate, int pts_per_block) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+    }
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* bas = sbas_all + (size_t)warp * pl.B;
+    int* idx = reinterpret_cast<int*>(sbas_all + (size_t)n_warps * pl.B) + (size_t)warp * pl.E;
+    __syncthreads();
+
+    // lane owns columns tile*64*CPL2 + 64*c + 2*lane + {0, 1}, c < CPL2
+    const int64_t col0 = (int64_t)blockIdx.y * (64 * CPL2) + 2 * lane;
+    const double* fcol = f + col0;
+    const int64_t p_begin = (int64_t)blockIdx.x * pts_per_block;
+    const int64_t p_end = min(P, p_begin + pts_per_block);
+    for (int64_t p = p_begin + warp; p < p_end; p += n_warps) {
+        const double* xp = x + p * ldx;
+        __syncwarp();
+        for (int e = lane; e < pl.E; e += 32) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, int>(en, xp[en.dim], sknots, slambda, bas, idx, e, 1, pl.flags);
+        }
+        __syncwarp();
+        double2 acc[CPL2];
+#pragma unroll
+        for (int c = 0; c < CPL2; ++c) acc[c] = make_double2(0.0, 0.0);
+        for (int t = 0; t < pl.T; ++t) {
+            const TermHdr h = pl.hdr[t];
+            const double coef = pl.coeff[t];
+            const TermDim* td = pl.tdim + h.dim_off;
+            const int* tmap = pl.maps + h.val_off;
+            double2 tp[CPL2];
+            if (h.k == 0) {
+                const double* fr = fcol + (int64_t)tmap[0] * ldf;
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) tp[c] = __ldg(reinterpret_cast<const double2*>(fr + 64 * c));
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) tp[c] = make_double2(0.0, 0.0);
+                for (int c_base = 0; c_base < h.ncorner; c_base += 32) {
+                    const int cid = c_base + lane;
+                    double w = 1.0;
+                    int row = 0;
+                    if (cid < h.ncorner) {
+                        int off = 0;
+                        if (KIND == SGM_LAGRANGE) {
+                            int cs = h.ncorner;
+                            for (int j = 0; j < h.k; ++j) {
+                                const TermDim d = td[j];
+                                cs /= d.radix;
+                                const int a = (cid / cs) % d.radix;
+                                w = w * digit_weight<KIND>(bas, 1, d, a);
+                                off += (idx[d.ent] + a) * d.stride;
+                            }
+                        } else {
+                            constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
+                            int cs = h.ncorner;
+                            int rem = cid;
+                            for (int j = 0; j < h.k; ++j) {
+                                const TermDim d = td[j];
+                                cs /= R;
+                                const int a = rem / cs;
+                                rem -= a * cs;
+                                w = w * digit_weight<KIND>(bas, 1, d, a);
+                                off += (idx[d.ent] + a) * d.stride;
+                            }
+                        }
+                        row = tmap[off];
+                    }
+                    const int n_in = min(32, h.ncorner - c_base);
+                    for (int cc = 0; cc < n_in; ++cc) {
+                        const double wv = __shfl_sync(0xffffffffu, w, cc);
+                        const int r = __shfl_sync(0xffffffffu, row, cc);
+                        const double* fr = fcol + (int64_t)r * ldf;
+                        double2 v[CPL2];
+#pragma unroll
+                        for (int c = 0; c < CPL2; ++c)
+                            v[c] = __ldg(reinterpret_cast<const double2*>(fr + 64 * c));
+#pragma unroll
+                        for (int c = 0; c < CPL2; ++c) {
+                            tp[c].x = tp[c].x + v[c].x * wv;
+                            tp[c].y = tp[c].y + v[c].y * wv;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CPL2; ++c) {
+                acc[c].x = acc[c].x + coef * tp[c].x;
+                acc[c].y = acc[c].y + coef * tp[c].y;
+            }
+        }
+        double* o = out + p * ldo + col0;
+#pragma unroll
+        for (int c = 0; c < CPL2; ++c) {
+            double2* dst = reinterpret_cast<double2*>(o + 64 * c);
+            double2 r = make_double2(scale * acc[c].x, scale * acc[c].y);
+            if (accumulate) {
+                const double2 old = *dst;
+                r.x = old.x + r.x;
+                r.y = old.y + r.y;
+            }
+            *dst = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Brownian-motion expansions (parametric_expansions_brownian_motion.py:17-91)
 // ---------------------------------------------------------------------------------------
 // One hat per level contains s = t/T; all other hats of the level contribute an exact 0 in
