@@ -77,6 +77,20 @@ def algorithmic_bytes(it, P, NF):
     return 8 * P * it.N + 8 * P * NF + 8 * it.num_nodes * NF + tables
 
 
+def secondary_rooflines(P, corners, terms, kernel_ms, clk):
+    """Lower bounds of the exact pw-linear scalar kernel on the on-chip resources that
+    actually bind it (148 SMs): L1 data pipe 128 B/clk/SM moves one 8-byte value per corner
+    (2 wavefronts per warp-wide 64-bit gather at best), FP64 pipe 64 lanes/clk/SM executes
+    ~4 operations per corner (weight product, value product, add, amortised prefix)."""
+    mhz = (clk.get("sm_mhz") or 1965.0) * 1e6
+    sms = 148
+    t_l1 = P * corners * 8 / (128 * sms * mhz)
+    t_fp64 = P * corners * 4 / (64 * sms * mhz)
+    t = kernel_ms * 1e-3
+    return {"l1_data_pipe_floor_ms": t_l1 * 1e3, "fp64_floor_ms": t_fp64 * 1e3,
+            "frac_of_l1_floor": t_l1 / t, "frac_of_fp64_floor": t_fp64 / t}
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -353,9 +367,14 @@ def main():
                          "kernel": "sgm::eval_points_split_kernel<pw-linear,16,64> (+ pregather and "
                                    "the point locality sort, ~1% of the step)",
                          "kernel_ms": kernel_ms,
-                         "note": "direct combination form is bound by on-chip gathers and FP64 "
-                                 "issue, not HBM (DESIGN.md): secondary figures below",
-                         "corner_gathers_per_s": P * corners / (kernel_ms * 1e-3)},
+                         "note": "the exact combination form is bound by the SM's L1 data pipe "
+                                 "(128 B/clk/SM; 8-byte corner gathers + bracket tables) and "
+                                 "FP64 issue, not HBM (DESIGN.md section 5); ncu of this kernel: "
+                                 "L1 data pipe 78 %, issue 54 %, FP64 pipe 35 % of peak "
+                                 "(profiles/r1_v3_split_sorted_ncu_full.txt)",
+                         "corner_gathers_per_s": P * corners / (kernel_ms * 1e-3),
+                         "secondary": secondary_rooflines(P, corners, len(it._coeffs),
+                                                          kernel_ms, clocks.summary())},
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,
         }

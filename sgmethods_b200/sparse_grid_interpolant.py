@@ -230,6 +230,28 @@ class SGInterpolant:
                 device=device)
         return self._device_plans[device]
 
+    def _interpolate_pipelined(self, torch, plan, x_host, f, device):
+        """Pinned host points: copy them in chunks on a side stream while the previous chunk
+        is being evaluated (the kernels stay on the current stream, in order)."""
+        P, NF = x_host.shape[0], f.shape[1]
+        out = torch.empty((P, NF), dtype=torch.float64, device=device)
+        compute = torch.cuda.current_stream(device)
+        copier = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device)
+        copier.wait_stream(compute)
+        staged = []
+        for lo in range(0, P, _H2D_CHUNK):
+            hi = min(P, lo + _H2D_CHUNK)
+            with torch.cuda.stream(copier):
+                xd = x_host[lo:hi, :self.N].to(device, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copier)
+            staged.append((lo, hi, xd, done))
+        for lo, hi, xd, done in staged:
+            compute.wait_event(done)
+            xd.record_stream(compute)
+            plan.eval(xd, f, out[lo:hi])
+        return out
+
     def _check_operator_constraints(self):
         if self._kind == _lib.KIND_CUBIC and self._fam_m.size and self._fam_m.min() < 4:
             # reference: UnboundLocalError in TPPwCubicInterpolator.__call__ (:232)
@@ -250,22 +272,30 @@ class SGInterpolant:
             device = x_new.device if x_new.is_cuda else torch.device("cuda", torch.cuda.current_device())
         else:
             device = torch.device("cuda", torch.cuda.current_device())
-        x = _to_device(torch, x_new, device)
+        n_used = int((self._num_nodes > 1).any(axis=0).nonzero()[0].max() + 1) \
+            if (self._num_nodes > 1).any() else 0
         f = _to_device(torch, f_on_SG, device)
-        if x.dim() == 1:
-            x = x.reshape(-1, 1)
         if f.dim() != 2:
             raise IndexError("f_on_SG must be 2-D (num_nodes, dim_f)")     # reference: tuple index out of range
         if f.shape[0] < self.num_nodes:
             raise IndexError(f"f_on_SG has {f.shape[0]} rows, the sparse grid {self.num_nodes}")
-        n_used = int((self._num_nodes > 1).any(axis=0).nonzero()[0].max() + 1) \
-            if (self._num_nodes > 1).any() else 0
-        if x.shape[1] < n_used:
-            raise IndexError(f"x_new has {x.shape[1]} columns, the interpolant uses {n_used}")
-        if x.shape[1] < self.N:          # unused trailing directions: pad so that ldx >= N
-            x = torch.nn.functional.pad(x, (0, self.N - x.shape[1]))
         plan = self.device_plan(device.index)
-        out = plan.eval(x, f)
+        host_rows = x_new.shape[0] if hasattr(x_new, "shape") and len(x_new.shape) == 2 else 0
+        pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
+            x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
+        if pinned and host_rows >= 4 * _H2D_CHUNK:
+            out = self._interpolate_pipelined(torch, plan, x_new, f, device)
+        else:
+            if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):
+                x_new = x_new[:, :self.N]        # only the first N columns travel to the GPU
+            x = _to_device(torch, x_new, device)
+            if x.dim() == 1:
+                x = x.reshape(-1, 1)
+            if x.shape[1] < n_used:
+                raise IndexError(f"x_new has {x.shape[1]} columns, the interpolant uses {n_used}")
+            if x.shape[1] < self.N:      # unused trailing directions: pad so that ldx >= N
+                x = torch.nn.functional.pad(x, (0, self.N - x.shape[1]))
+            out = plan.eval(x, f)
         if self._kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
                              "(or is NaN); the reference raises IndexError here "
@@ -273,6 +303,9 @@ class SGInterpolant:
         if as_torch:
             return out.squeeze()
         return np.squeeze(out.cpu().numpy())
+
+
+_H2D_CHUNK = 131072      # rows per host->device chunk of the pipelined path
 
 
 def _to_device(torch, a, device):

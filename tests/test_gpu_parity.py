@@ -340,3 +340,16 @@ def test_error_indicators_against_oracle():
                                      lambda y: (calls.append(1), f(y))[1], cur.SG, u_on_SG, yy,
                                      norm, u_interp)
     assert np.array_equal(again[:-1], got[:-1] + 1.0) and abs(again[-1] - got[-1]) < 1e-14
+
+
+def test_pipelined_host_path_equals_device_path():
+    """Pinned host points take the chunked copy/compute pipeline; same bits as one launch."""
+    import torch
+    it = SGInterpolant(mis.smolyak_mid_set(2, 6), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    P = 4 * 131072 + 777
+    xh = torch.randn((P, 9), dtype=torch.float64).pin_memory()       # 3 unused columns
+    f = torch.randn((it.num_nodes, 1), dtype=torch.float64)
+    got = it.interpolate(xh, f)
+    ref = it.interpolate(xh.cuda(), f.cuda())
+    assert got.is_cuda and torch.equal(got, ref)
