@@ -79,10 +79,13 @@ class DevicePlan:
         """x (P, >=N), f (M, NF), both fp64 CUDA tensors on this plan's device -> (P, NF)."""
         torch = torch_cuda()
         assert x.is_cuda and f.is_cuda and x.dtype == torch.float64 and f.dtype == torch.float64
-        assert x.dim() == 2 and f.dim() == 2 and x.stride(1) == 1 and f.stride(1) == 1
+        assert x.dim() == 2 and f.dim() == 2
         P, NF = x.shape[0], f.shape[1]
         if out is None:
             out = torch.empty((P, NF), dtype=torch.float64, device=x.device)
+        if P == 0 or NF == 0:
+            return out
+        assert (x.shape[1] == 1 or x.stride(1) == 1) and (NF == 1 or f.stride(1) == 1)
         ws = self.workspace(P, NF)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(_lib.load().sgm_eval(

@@ -353,3 +353,84 @@ def test_pipelined_host_path_equals_device_path():
     got = it.interpolate(xh, f)
     ref = it.interpolate(xh.cuda(), f.cuda())
     assert got.is_cuda and torch.equal(got, ref)
+
+
+# ------------------------------------------------------------------------------ edge cases
+def test_empty_ragged_and_strided_inputs():
+    import torch
+    it = SGInterpolant(mis.smolyak_mid_set(3, 3), nodes_1d.cc_nodes,
+                       lambda n: np.where(n == 0, 1, 2 ** n + 1), verbose=False)
+    plan = oracle_plan_of(it)
+    rng = np.random.default_rng(5)
+    f = rng.normal(size=(it.num_nodes, 5))
+    # no points
+    assert it.interpolate(np.zeros((0, 3)), f).shape == (0, 5)
+    assert it.interpolate(np.zeros((0, 3)), f[:, :1]).shape == (0,)
+    # one point, and point counts around the 32-point tile / 8-warp block boundaries
+    for P in (1, 31, 32, 33, 63, 65, 257):
+        x = rng.uniform(-1, 1, (P, 3))
+        for cols in (1, 5):
+            ref = sg_oracle.interpolate(plan, x, f[:, :cols], squeeze=False)
+            got = np.asarray(it.interpolate(x, f[:, :cols])).reshape(ref.shape)
+            assert np.array_equal(got, ref), (P, cols)
+    # non-contiguous views: strided rows of x, column slice of f, extra rows in f
+    xbig = rng.uniform(-1, 1, (40, 7))
+    fbig = rng.normal(size=(it.num_nodes + 3, 9))
+    ref = sg_oracle.interpolate(plan, xbig[::2, :3], fbig[:it.num_nodes, 2:6], squeeze=False)
+    got = it.interpolate(torch.from_numpy(xbig).cuda()[::2], torch.from_numpy(fbig).cuda()[:, 2:6])
+    assert np.array_equal(got.cpu().numpy(), ref)
+    # 1-D x is one column (reference wrapper, tp_interpolant_wrapper.py:54-55)
+    it1 = SGInterpolant(mis.smolyak_mid_set(3, 1), nodes_1d.cc_nodes,
+                        lambda n: np.where(n == 0, 1, 2 ** n + 1), verbose=False)
+    f1 = rng.normal(size=(it1.num_nodes, 1))
+    x1 = rng.uniform(-1, 1, 17)
+    assert np.array_equal(it1.interpolate(x1, f1),
+                          sg_oracle.interpolate(oracle_plan_of(it1), x1, f1))
+    # too few rows in f / wrong rank
+    with pytest.raises(IndexError):
+        it.interpolate(np.zeros((2, 3)), f[:10])
+    with pytest.raises(IndexError):
+        it.interpolate(np.zeros((2, 3)), f[:, 0])
+
+
+def test_vector_outputs_across_column_tile_boundaries():
+    """NF around the 32/64/128/256-column tile sizes of the column kernels (wide kernel +
+    guarded remainder), odd leading dimensions (unaligned rows fall back to 8-byte loads)."""
+    import torch
+    it = SGInterpolant(mis.smolyak_mid_set(3, 4), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    plan = oracle_plan_of(it)
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=(37, 4))
+    fall = rng.normal(size=(it.num_nodes, 700))
+    for NF in (2, 31, 33, 64, 127, 128, 129, 255, 256, 257, 511, 513, 700):
+        ref = sg_oracle.interpolate(plan, x, fall[:, :NF], squeeze=False)
+        got = it.interpolate(x, np.ascontiguousarray(fall[:, :NF])).reshape(ref.shape)
+        assert np.array_equal(got, ref), NF
+    # a view with odd leading dimension and odd column offset: rows are not 16-byte aligned
+    fd = torch.from_numpy(fall).cuda()
+    ref = sg_oracle.interpolate(plan, x, fall[:, 1:300], squeeze=False)
+    got = it.interpolate(torch.from_numpy(x).cuda(), fd[:, 1:300])
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_term_sharding_plan_slices_on_one_gpu():
+    """mode='terms' building block: evaluating contiguous term ranges with separate plans and
+    adding the partial results reproduces the full interpolant to rounding."""
+    import torch
+    from sgmethods_b200._device import DevicePlan
+    it = SGInterpolant(mis.smolyak_mid_set(3, 5), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    rng = np.random.default_rng(8)
+    x = torch.from_numpy(rng.normal(size=(200, 5))).cuda()
+    f = torch.from_numpy(rng.normal(size=(it.num_nodes, 1))).cuda()
+    full = it.device_plan().eval(x, f)
+    T = len(it._coeffs)
+    total = torch.zeros_like(full)
+    for t0, t1 in ((0, T // 3), (T // 3, T // 2), (T // 2, T)):
+        lo, hi = it._map_off[t0], it._map_off[t1]
+        part = DevicePlan(it._kind, it.N, it.num_nodes, it._coeffs[t0:t1].astype(float),
+                          it._term_fam[t0:t1], it._map_off[t0:t1 + 1] - lo, it._maps[lo:hi],
+                          it._fam_off, it._fam_knots)
+        total += part.eval(x, f)
+    assert float((total - full).abs().max()) <= 1e-12 * float(full.abs().max())
