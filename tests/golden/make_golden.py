@@ -191,6 +191,17 @@ def main():
     interp_case("lin_c2_small", Lam, n1d.unbounded_nodes_nested,
                 lambda n: 2 ** (n + 1) - 1, "linear", x, f_on_SG=fsg)
 
+    # (13) Gaussian weighted-Leja knots shipped by the reference as .mat data (config 2
+    #      wording), Lagrange operator, lev2knots = nu + 1 (nested for every n)
+    from scipy.io import loadmat
+    X = loadmat("/root/reference/sgmethods/knots_weighted_leja_guass.mat")["X"].reshape(-1)
+    leja = lambda n: np.sort(X[:int(n)])  # noqa: E731
+    Lam = mis.smolyak_mid_set(4, 4)
+    x = rng.normal(0, 1, (48, 4))
+    interp_case("lag_leja_gauss", Lam, leja, lambda nu: nu + 1, "lagrange", x,
+                f=lambda y: np.array([np.exp(-0.2 * y @ y) * np.cos(y[0])]),
+                extra=dict(leja_X=X[:12]))
+
     # ---- sample_on_SG recycling (sparse_grid_interpolant.py:141-250) --------------------
     l2k = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa
     fvec = lambda y: np.array([np.sin(np.sum(y)), np.sum(y * y)])  # noqa

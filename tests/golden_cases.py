@@ -18,6 +18,7 @@ CASES = {
     "lag_hermite": ("hermite", "n+1", "lagrange"),
     "lin_example1": ("unb", "2^(n+1)-1", "linear"),
     "lin_c2_small": ("unb", "2^(n+1)-1", "linear"),
+    "lag_leja_gauss": ("leja", "n+1", "lagrange"),
 }
 
 LEV2KNOTS = {
@@ -31,6 +32,12 @@ LEV2KNOTS = {
 
 def knot_family(name, nodes_module):
     n1d = nodes_module
+    if name == "leja":          # the first points of the reference's Gaussian Leja sequence
+        import os
+        from sgmethods_b200.leja import leja_knots
+        here = os.path.dirname(os.path.abspath(__file__))
+        with np.load(os.path.join(here, "golden", "lag_leja_gauss.npz")) as z:
+            return leja_knots(z["leja_X"])
     return {
         "equi": n1d.equispaced_nodes,
         "equi_arr": lambda n: np.atleast_1d(np.asarray(n1d.equispaced_nodes(n), dtype=float)),
