@@ -5,24 +5,61 @@ Same function name and argument list as the reference's
 sgmethods/compute_error_indicators.py (compute_GG_indicators_RM :16-121).  The reference is
 broken as shipped (it reads ``mid_set.reducedMargin`` / ``mid_set.midSet``; MidSet defines
 ``reduced_margin`` / ``mid_set``); this module implements the
-documented behaviour.  For every multi-index nu of the reduced margin that has no recycled
+documented behaviour: for every multi-index nu of the reduced margin that has no recycled
 value, the indicator is  L2_err_param( I_{Lambda + nu}[u](yy_rnd), u_interp ).
 
-B200 design: the extended interpolant of every candidate is built with the O(sum S_t) native
-table builder (the reference rebuilds an O(M^2) interpolant per candidate), samples are
-recycled through the hashed row matcher, the random points are uploaded once and every
-candidate is evaluated by the fused kernel.  ``f`` and ``L2_err_param`` stay host callbacks.
+Two evaluation methods (keyword ``method``):
+
+  * ``"surplus"`` (default): I_{Lambda+nu}[u] - I_Lambda[u] is the hierarchical surplus
+    Delta_nu u = sum_{e in {0,1}^N, e <= supp(nu)} (-1)^{|e|} TP_{nu-e}[u], i.e. only 2^{|supp nu|}
+    tensor-product terms.  Each candidate gets a tiny plan with exactly those terms (built
+    by the O(sum S_t) native table builder), samples on nodes that already belong to the
+    current sparse grid are recycled through the hashed row matcher, only the new nodes of
+    TP_nu call ``f``, and ``u_interp + Delta_nu u`` is formed on the GPU.  Cost per candidate:
+    2^k terms instead of re-evaluating all terms of the extended interpolant.
+  * ``"rebuild"``: the reference's own sequence (extended SGInterpolant, recycled sampling,
+    full evaluation) with the fast constructor and the fused kernel.
+
+Both agree to rounding; "surplus" does not re-sum the large alternating combination sum, so
+it is the more accurate of the two when the indicator is small.  ``f`` and
+``L2_err_param`` stay host callbacks in either case.
 """
+from itertools import product
+
 import numpy as np
 
-from .sparse_grid_interpolant import SGInterpolant
-from .tp_inteprolants import TPPwLinearInterpolator
+from . import _lib
+from .sparse_grid_interpolant import NODE_TOL, SGInterpolant, _to_device
+from .tp_inteprolants import TPPwLinearInterpolator, resolve_kind
 from .utils import find_mid, lexic_sort
+
+
+def _surplus_tables(nu, knots, lev2knots):
+    """Packed tables of Delta_nu = sum_e (-1)^{|e|} TP_{nu-e}: (coeffs, num_nodes, fam_m,
+    fam_off, fam_knots, term_fam, grid)."""
+    supp = np.flatnonzero(nu > 0)
+    rows, coeffs = [], []
+    for bits in product((0, 1), repeat=supp.size):
+        e = np.zeros_like(nu)
+        e[supp] = bits
+        rows.append(lev2knots(nu - e).astype(int))
+        coeffs.append(-1.0 if sum(bits) % 2 else 1.0)
+    num_nodes = np.asarray(rows, dtype=np.int32).reshape(len(rows), nu.size)
+    fam_m = np.unique(num_nodes[num_nodes > 1]).astype(np.int32)
+    fam_list = [np.atleast_1d(np.asarray(knots(np.int64(m)), dtype=np.float64)) for m in fam_m]
+    fam_off = np.concatenate(([0], np.cumsum(fam_m, dtype=np.int64))).astype(np.int64)
+    fam_knots = np.concatenate(fam_list) if fam_list else np.zeros(0)
+    lut = np.full(int(fam_m.max()) + 1 if fam_m.size else 2, -1, dtype=np.int32)
+    lut[fam_m] = np.arange(fam_m.size, dtype=np.int32)
+    term_fam = np.where(num_nodes > 1, lut[np.minimum(num_nodes, lut.size - 1)], -1)
+    grid = _lib.HostGrid(num_nodes, fam_m, fam_off, fam_knots, NODE_TOL)
+    return np.asarray(coeffs), term_fam.astype(np.int32), fam_off, fam_knots, grid
 
 
 def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
                              f, SG, u_on_SG, yy_rnd, L2_err_param, u_interp,
-                             TP_inteporlant=TPPwLinearInterpolator, n_parallel=1):
+                             TP_inteporlant=TPPwLinearInterpolator, n_parallel=1,
+                             method="surplus"):
     """Args as in the reference: old reduced margin and its indicators (recycled where the
     index is still in the reduced margin), the current MidSet, knots / lev2knots, the
     function ``f``, the current sparse grid ``SG`` with the values ``u_on_SG``, random
@@ -30,6 +67,7 @@ def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
     interpolant's values ``u_interp`` on ``yy_rnd``.  Returns one indicator per row of
     ``mid_set.reduced_margin``."""
     assert old_RM.shape[0] == old_estimators.size
+    assert method in ("surplus", "rebuild")
     reduced_margin = mid_set.reduced_margin
     card_rm = reduced_margin.shape[0]
     indicators = np.zeros(card_rm)
@@ -48,19 +86,56 @@ def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
                 indicators[i] = old_estimators[pos]
             else:
                 to_compute.append(i)
+    if not to_compute:
+        return indicators
 
-    yy_dev = None
-    if to_compute:                             # keep the random points resident on the GPU
-        from ._device import torch_cuda
-        from .sparse_grid_interpolant import _to_device
-        torch = torch_cuda()
-        yy_dev = _to_device(torch, yy_rnd, torch.device("cuda", torch.cuda.current_device()))
+    from ._device import DevicePlan, torch_cuda
+    torch = torch_cuda()
+    device = torch.device("cuda", torch.cuda.current_device())
+    yy_dev = _to_device(torch, yy_rnd, device)           # random points stay on the GPU
+    if yy_dev.dim() == 1:
+        yy_dev = yy_dev.reshape(-1, 1)
+    N = reduced_margin.shape[1]
+    if yy_dev.shape[1] < N:
+        yy_dev = torch.nn.functional.pad(yy_dev, (0, N - yy_dev.shape[1]))
+
+    if method == "rebuild":
+        for i in to_compute:
+            nu = reduced_margin[i, :]
+            extended = lexic_sort(np.vstack((mid_set.mid_set, nu)))
+            interp_ext = SGInterpolant(extended, knots, lev2knots, tp_interpolant=TP_inteporlant,
+                                       n_parallel=n_parallel, verbose=False)
+            u_on_SG_ext = interp_ext.sample_on_SG(f, old_xx=SG, old_samples=u_on_SG)
+            u_interp_ext = interp_ext.interpolate(yy_dev, u_on_SG_ext)
+            indicators[i] = L2_err_param(u_interp_ext.cpu().numpy(), u_interp)
+        return indicators
+
+    kind = resolve_kind(TP_inteporlant)
+    u_on_SG = np.atleast_2d(np.asarray(u_on_SG, dtype=np.float64))
+    SG_cur = np.asarray(SG, dtype=np.float64)
+    if SG_cur.shape[1] < N:          # the current grid lives in fewer dimensions: embed it
+        SG_cur = np.hstack((SG_cur, np.zeros((SG_cur.shape[0], N - SG_cur.shape[1]))))
+    u_cur = np.asarray(u_interp, dtype=np.float64)
+    u_cur_dev = torch.from_numpy(np.ascontiguousarray(u_cur.reshape(yy_dev.shape[0], -1))).to(device)
     for i in to_compute:
-        nu = reduced_margin[i, :]
-        extended = lexic_sort(np.vstack((mid_set.mid_set, nu)))
-        interp_ext = SGInterpolant(extended, knots, lev2knots, tp_interpolant=TP_inteporlant,
-                                   n_parallel=n_parallel, verbose=False)
-        u_on_SG_ext = interp_ext.sample_on_SG(f, old_xx=SG, old_samples=u_on_SG)
-        u_interp_ext = interp_ext.interpolate(yy_dev, u_on_SG_ext)
-        indicators[i] = L2_err_param(u_interp_ext.cpu().numpy(), u_interp)
+        nu = np.asarray(reduced_margin[i, :])
+        coeffs, term_fam, fam_off, fam_knots, grid = _surplus_tables(nu, knots, lev2knots)
+        map_off, maps = grid.maps()
+        nodes = grid.nodes_dense()
+        # values on the nodes of the 2^k surplus terms: recycle what the current grid has
+        match = _lib.match_rows(nodes, SG_cur, NODE_TOL)
+        vals = np.zeros((nodes.shape[0], u_on_SG.shape[1]))
+        have = match >= 0
+        vals[have] = u_on_SG[match[have]]
+        for r in np.flatnonzero(~have):
+            vals[r, :] = f(nodes[r, :])
+        plan = DevicePlan(kind, N, nodes.shape[0], coeffs, term_fam, map_off, maps, fam_off,
+                          fam_knots, device=device.index)
+        surplus = plan.eval(yy_dev, torch.from_numpy(vals).to(device))
+        if kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
+            raise IndexError("pw-quadratic interpolation: a point lies right of the last knot")
+        u_ext = (u_cur_dev + surplus).cpu().numpy().reshape(u_cur.shape)
+        indicators[i] = L2_err_param(u_ext, u_interp)
+        plan.close()
+        grid.close()
     return indicators

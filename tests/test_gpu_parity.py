@@ -327,13 +327,18 @@ def test_error_indicators_against_oracle():
     u_on_SG = cur.sample_on_SG(f)
     yy = np.random.default_rng(3).normal(size=(500, ms.get_dim()))
     u_interp = cur.interpolate(yy, u_on_SG)
-    got = compute_GG_indicators_RM(np.zeros((0, 0), dtype=int), np.zeros(0), ms, knots, lev, f,
-                                   cur.SG, u_on_SG, yy, norm, u_interp)
     ref = drivers_oracle.gg_indicators(ms.mid_set, ms.reduced_margin, knots, lev, f, cur.SG,
                                        u_on_SG, yy, norm, u_interp)
-    assert got.shape == (ms.get_cardinality_reduced_margin(),)
-    assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
-    assert np.all(got > 0)
+    scale = max(1.0, float(np.max(np.abs(u_interp))))
+    for method, tol in (("rebuild", 1e-12), ("surplus", 1e-11)):
+        calls = []
+        got = compute_GG_indicators_RM(np.zeros((0, 0), dtype=int), np.zeros(0), ms, knots, lev,
+                                       lambda y: (calls.append(1), f(y))[1], cur.SG, u_on_SG, yy,
+                                       norm, u_interp, method=method)
+        assert got.shape == (ms.get_cardinality_reduced_margin(),)
+        assert np.max(np.abs(got - ref)) <= tol * scale, (method, np.max(np.abs(got - ref)))
+        assert np.all(got > 0)
+        print(method, "f evaluations:", len(calls), "max dev", np.max(np.abs(got - ref)))
     # recycling: unchanged reduced-margin entries are copied, not recomputed
     calls = []
     again = compute_GG_indicators_RM(ms.reduced_margin[:-1], got[:-1] + 1.0, ms, knots, lev,
