@@ -382,7 +382,7 @@ def main():
             line["final_all_gather"] = {"ms": gather_ms, "bytes_per_rank": int(P * NF * 8),
                                         "backend": "nccl all_gather_into_tensor",
                                         "in_timed_step": False}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or cores * 1024
             v, used, dt, what = cpu_reference_rate(it, KIND_NAME[it._kind], NF, sample,
