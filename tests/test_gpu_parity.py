@@ -439,3 +439,16 @@ def test_term_sharding_plan_slices_on_one_gpu():
                           it._fam_off, it._fam_knots)
         total += part.eval(x, f)
     assert float((total - full).abs().max()) <= 1e-12 * float(full.abs().max())
+
+
+def test_wrapper_shim_matches_reference_semantics():
+    from sgmethods_b200.tp_interpolant_wrapper import TPInterpolatorWrapper
+    rng = np.random.default_rng(4)
+    nodes = (np.linspace(-1, 1, 5), np.linspace(-1, 1, 3))
+    vals = rng.normal(size=(5, 3, 2))
+    x = rng.uniform(-1, 1, (20, 6))
+    w = TPInterpolatorWrapper(nodes, np.array([1, 4]), vals, TPPwLinearInterpolator)
+    assert rel_err(w(x), sg_oracle.tp_linear(nodes, vals, x[:, [1, 4]])) <= TOL
+    const = TPInterpolatorWrapper((0,), np.array([], dtype=int), np.array([[3.0, -1.0]]),
+                                  TPPwLinearInterpolator)
+    assert np.array_equal(const(x), np.tile([[3.0, -1.0]], (20, 1)))
