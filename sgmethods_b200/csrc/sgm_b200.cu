@@ -294,7 +294,7 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (ldf % 2 == 0) && (ldo % 2 == 0);
     const char* nowide = std::getenv("SGM_NO_WIDE");          // dev knob
-    if (aligned && !nowide && NF >= 128) {
+    if (aligned && !nowide && NF >= 128 && plan->dev.n_corners > 0) {
         const int tile = NF >= 512 ? 256 : 128;
         const int64_t n_tiles = NF / tile;
         int rc = tile == 256
@@ -494,13 +494,31 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     std::vector<double> knots(desc->fam_knots, desc->fam_knots + n_knots);
     std::vector<double> lambda;
     if (kind == SGM_LAGRANGE) lambda.assign(desc->fam_lambda, desc->fam_lambda + n_knots);
+    // global corner list for the wide column kernel (skipped when absurdly long)
+    std::vector<int> corner_term, corner_off;
+    if (corners > 0 && corners < ((int64_t)1 << 27)) {
+        corner_off.resize(T + 1);
+        corner_term.reserve((size_t)corners);
+        int64_t run = 0;
+        for (int64_t t = 0; t < T; ++t) {
+            corner_off[t] = (int)run;
+            for (int c = 0; c < hdr[t].ncorner; ++c) corner_term.push_back((int)t);
+            run += hdr[t].ncorner;
+        }
+        corner_off[T] = (int)run;
+        d.n_corners = (int)run;
+    } else {
+        d.n_corners = 0;
+    }
     std::vector<unsigned> flags(4, 0u);
     int rc = SGM_OK;
     const unsigned* cflags = nullptr;
     if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
         (rc = upload(plan, rec, &d.rec)) ||
         (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
-        (rc = upload(plan, maps, &d.maps)) || (rc = upload(plan, knots, &d.knots)) ||
+        (rc = upload(plan, maps, &d.maps)) ||
+        (rc = upload(plan, corner_term, &d.corner_term)) ||
+        (rc = upload(plan, corner_off, &d.corner_off)) || (rc = upload(plan, knots, &d.knots)) ||
         (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, flags, &cflags))) {
         sgm_plan_destroy(plan);
         return rc;

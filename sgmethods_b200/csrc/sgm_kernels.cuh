@@ -56,6 +56,9 @@ struct PlanDev {
     const double* coeff;
     const Entry* ent;
     const int* maps;
+    const int* corner_term;            // term of every entry of the global corner list
+    const int* corner_off;             // T+1 prefix sums of the terms' corner counts
+    int n_corners;                     // sum_t C_t (0 if the list is not built)
     const double* knots;
     const double* lambda;
     unsigned* flags;
@@ -676,73 +679,76 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
             fill_basis<KIND, int>(en, xp[en.dim], sknots, slambda, bas, idx, e, 1, pl.flags);
         }
         __syncwarp();
-        double2 acc[CPL2];
+        double2 acc[CPL2], tp[CPL2];
 #pragma unroll
-        for (int c = 0; c < CPL2; ++c) acc[c] = make_double2(0.0, 0.0);
-        for (int t = 0; t < pl.T; ++t) {
-            const TermHdr h = pl.hdr[t];
-            const double coef = pl.coeff[t];
-            const TermDim* td = pl.tdim + h.dim_off;
-            const int* tmap = pl.maps + h.val_off;
-            double2 tp[CPL2];
-            if (h.k == 0) {
-                const double* fr = fcol + (int64_t)tmap[0] * ldf;
-#pragma unroll
-                for (int c = 0; c < CPL2; ++c) tp[c] = __ldg(reinterpret_cast<const double2*>(fr + 64 * c));
-            } else {
-#pragma unroll
-                for (int c = 0; c < CPL2; ++c) tp[c] = make_double2(0.0, 0.0);
-                for (int c_base = 0; c_base < h.ncorner; c_base += 32) {
-                    const int cid = c_base + lane;
-                    double w = 1.0;
-                    int row = 0;
-                    if (cid < h.ncorner) {
-                        int off = 0;
-                        if (KIND == SGM_LAGRANGE) {
-                            int cs = h.ncorner;
-                            for (int j = 0; j < h.k; ++j) {
-                                const TermDim d = td[j];
-                                cs /= d.radix;
-                                const int a = (cid / cs) % d.radix;
-                                w = w * digit_weight<KIND>(bas, 1, d, a);
-                                off += (idx[d.ent] + a) * d.stride;
-                            }
-                        } else {
-                            constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
-                            int cs = h.ncorner;
-                            int rem = cid;
-                            for (int j = 0; j < h.k; ++j) {
-                                const TermDim d = td[j];
-                                cs /= R;
-                                const int a = rem / cs;
-                                rem -= a * cs;
-                                w = w * digit_weight<KIND>(bas, 1, d, a);
-                                off += (idx[d.ent] + a) * d.stride;
-                            }
-                        }
-                        row = tmap[off];
+        for (int c = 0; c < CPL2; ++c) {
+            acc[c] = make_double2(0.0, 0.0);
+            tp[c] = make_double2(0.0, 0.0);
+        }
+        // The corner contributions of ALL terms form one list (term order, C order inside a
+        // term).  32 lanes set up 32 consecutive entries of the list at a time -- possibly
+        // belonging to several small terms -- then the warp walks them in order; when the
+        // last corner of a term has been added, out = out + c_t * tp is applied and tp reset.
+        for (int g0 = 0; g0 < pl.n_corners; g0 += 32) {
+            const int g = g0 + lane;
+            double w = 1.0, coef = 0.0;
+            int row = 0, last = 0;
+            if (g < pl.n_corners) {
+                const int t = pl.corner_term[g];
+                const TermHdr h = pl.hdr[t];
+                const int cid = g - pl.corner_off[t];
+                const TermDim* td = pl.tdim + h.dim_off;
+                int off = 0;
+                if (KIND == SGM_LAGRANGE) {
+                    int cs = h.ncorner;
+                    for (int j = 0; j < h.k; ++j) {
+                        const TermDim d = td[j];
+                        cs /= d.radix;
+                        const int a = (cid / cs) % d.radix;
+                        w = w * digit_weight<KIND>(bas, 1, d, a);
+                        off += (idx[d.ent] + a) * d.stride;
                     }
-                    const int n_in = min(32, h.ncorner - c_base);
-                    for (int cc = 0; cc < n_in; ++cc) {
-                        const double wv = __shfl_sync(0xffffffffu, w, cc);
-                        const int r = __shfl_sync(0xffffffffu, row, cc);
-                        const double* fr = fcol + (int64_t)r * ldf;
-                        double2 v[CPL2];
-#pragma unroll
-                        for (int c = 0; c < CPL2; ++c)
-                            v[c] = __ldg(reinterpret_cast<const double2*>(fr + 64 * c));
-#pragma unroll
-                        for (int c = 0; c < CPL2; ++c) {
-                            tp[c].x = tp[c].x + v[c].x * wv;
-                            tp[c].y = tp[c].y + v[c].y * wv;
-                        }
+                } else {
+                    constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
+                    int cs = h.ncorner;
+                    int rem = cid;
+                    for (int j = 0; j < h.k; ++j) {
+                        const TermDim d = td[j];
+                        cs /= R;
+                        const int a = rem / cs;
+                        rem -= a * cs;
+                        w = w * digit_weight<KIND>(bas, 1, d, a);
+                        off += (idx[d.ent] + a) * d.stride;
                     }
                 }
+                row = pl.maps[h.val_off + off];
+                last = (cid == h.ncorner - 1);
+                if (last) coef = pl.coeff[t];
             }
+            const int n_in = min(32, pl.n_corners - g0);
+            for (int cc = 0; cc < n_in; ++cc) {
+                const double wv = __shfl_sync(0xffffffffu, w, cc);
+                const int r = __shfl_sync(0xffffffffu, row, cc);
+                const int is_last = __shfl_sync(0xffffffffu, last, cc);
+                const double* fr = fcol + (int64_t)r * ldf;
+                double2 v[CPL2];
 #pragma unroll
-            for (int c = 0; c < CPL2; ++c) {
-                acc[c].x = acc[c].x + coef * tp[c].x;
-                acc[c].y = acc[c].y + coef * tp[c].y;
+                for (int c = 0; c < CPL2; ++c)
+                    v[c] = __ldg(reinterpret_cast<const double2*>(fr + 64 * c));
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) {
+                    tp[c].x = tp[c].x + v[c].x * wv;
+                    tp[c].y = tp[c].y + v[c].y * wv;
+                }
+                if (is_last) {
+                    const double cf = __shfl_sync(0xffffffffu, coef, cc);
+#pragma unroll
+                    for (int c = 0; c < CPL2; ++c) {
+                        acc[c].x = acc[c].x + cf * tp[c].x;
+                        acc[c].y = acc[c].y + cf * tp[c].y;
+                        tp[c] = make_double2(0.0, 0.0);
+                    }
+                }
             }
         }
         double* o = out + p * ldo + col0;
