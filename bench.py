@@ -35,6 +35,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes per launch of the evaluation kernel from the committed ncu capture
+# (136.91 MB read + 4.15 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
+NCU_TRAFFIC = {("c2", 10 ** 6): 141056000}
+
 METRIC = "interpolant point-evals x outputs per second (fp64)"
 UNIT = "point-evals*outputs/s"
 
@@ -190,6 +194,20 @@ def cpu_reference_rate(it, kind, NF, sample_points, seed=0, sampler="normal", re
             best = dt if best is None else min(best, dt)
     return sample_points * NF / best, len(chunks), best, \
         f"{sample_points} points of the workload split over {len(chunks)} processes"
+
+
+def cpu_single_core_rate(it, kind, NF, sample_points, sampler="normal"):
+    from oracle import sg_oracle
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(sample_points, it.N)) if sampler == "normal" else \
+        rng.uniform(-1, 1, (sample_points, it.N))
+    f = np.random.default_rng(1).normal(size=(it.num_nodes, NF))
+    plan = sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
+                                      it.active_tp_nodes_list, it.map_tp_to_SG)
+    t0 = time.perf_counter()
+    sg_oracle.interpolate(plan, x, f, "linear_scipy" if kind == "linear" else kind)
+    dt = time.perf_counter() - t0
+    return sample_points * NF / dt, dt
 
 
 KIND_NAME = {0: "linear", 1: "quadratic", 2: "cubic", 3: "lagrange"}
@@ -362,7 +380,11 @@ def main():
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
                     "d2h_bytes_per_step": int(P * NF * 8), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P)),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the "
+                         "kernel, ncu --set full capture of this command "
+                         "(profiles/r1_v3_split_sorted_ncu_full.txt)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel": "sgm::eval_points_split_kernel<pw-linear,16,64> (+ pregather and "
                                    "the point locality sort, ~1% of the step)",
@@ -389,6 +411,10 @@ def main():
                                                    sampler=sampler)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                                     "sample": what + f" ({dt:.1f} s)"}
+            # the reference as shipped is single-threaded: the same port on ONE core
+            v1, dt1 = cpu_single_core_rate(it, KIND_NAME[it._kind], NF, 1024, sampler)
+            line["cpu_baseline"]["single_core"] = {"value": v1, "cores": 1,
+                                                   "sample": f"1024 points, 1 process ({dt1:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
