@@ -452,3 +452,42 @@ def test_wrapper_shim_matches_reference_semantics():
     const = TPInterpolatorWrapper((0,), np.array([], dtype=int), np.array([[3.0, -1.0]]),
                                   TPPwLinearInterpolator)
     assert np.array_equal(const(x), np.tile([[3.0, -1.0]], (20, 1)))
+
+
+def test_every_scalar_kernel_flavour_against_oracle():
+    """Kernel selection paths of the scalar (NF = 1) evaluation: thread-per-point kernel
+    (few terms, many points), split kernel with the locality sort (>= 32768 points),
+    wide-linear flavour (terms with more than 4 active directions)."""
+    rng = np.random.default_rng(12)
+    # few terms + many points -> eval_points_kernel
+    it = SGInterpolant(mis.smolyak_mid_set(1, 3), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    x = rng.normal(size=(20000, 3))
+    f = rng.normal(size=(it.num_nodes, 1))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x, f)
+    assert np.array_equal(it.interpolate(x, f), ref)
+    # >= 32768 points -> counting sort + permuted tiles; check a subset against the oracle
+    it = SGInterpolant(mis.smolyak_mid_set(3, 5), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    x = rng.normal(size=(50001, 5))
+    f = rng.normal(size=(it.num_nodes, 1))
+    got = it.interpolate(x, f)
+    pick = rng.choice(50001, 600, replace=False)
+    assert np.array_equal(got[pick], sg_oracle.interpolate(oracle_plan_of(it), x[pick], f))
+    # k = 6 active directions -> nested-walk flavour of the pw-linear kernels
+    it = SGInterpolant(mis.tensor_product_mid_set(1, 6), nodes_1d.cc_nodes, lambda n: 2 * n + 1,
+                       verbose=False)
+    x = rng.uniform(-1.2, 1.2, (300, 6))
+    f = rng.normal(size=(it.num_nodes, 1))
+    assert np.array_equal(it.interpolate(x, f), sg_oracle.interpolate(oracle_plan_of(it), x, f))
+    x = rng.uniform(-1.2, 1.2, (40000, 6))
+    got = it.interpolate(x, f)
+    assert np.array_equal(got[:400], sg_oracle.interpolate(oracle_plan_of(it), x[:400], f))
+
+
+def test_levy_ciesielski_many_levels_uses_generic_kernel():
+    rng = np.random.default_rng(13)
+    tt = np.linspace(0, 1, 29)
+    yy = rng.normal(size=(3, 5000))                 # L = 13 > 12
+    W = param_LC_Brownian_motion(tt, yy, 1.0)
+    assert np.array_equal(W[1], brownian_oracle.lc_brownian(tt, yy[1], 1.0))
