@@ -45,7 +45,13 @@ typedef enum sgm_kind {
     SGM_PW_LINEAR = 0,        /* TPPwLinearInterpolator    tp_inteprolants.py:21-53   */
     SGM_PW_QUADRATIC = 1,     /* TPPwQuadraticInterpolator tp_inteprolants.py:55-160  */
     SGM_PW_CUBIC = 2,         /* TPPwCubicInterpolator     tp_inteprolants.py:162-277 */
-    SGM_LAGRANGE = 3          /* TPLagrangeInterpolator    tp_inteprolants.py:279-360 */
+    SGM_LAGRANGE = 3,         /* TPLagrangeInterpolator    tp_inteprolants.py:279-360 */
+    /* 4 is reserved (internal flavour).  Kind 5 has no reference class: it is the
+     * work-reduced HIERARCHICAL-SURPLUS form of the pw-linear interpolant on nested knots,
+     * sum over ALL multi-indices nu of surplus(nu, j(x)) * prod_d phi_{nu_d}(x_d) with one
+     * basis function per level and direction.  Mathematically equal to the combination
+     * formula, NOT bit-identical to it (it is the more accurate of the two); opt-in only. */
+    SGM_HIER_PW_LINEAR = 5
 } sgm_kind;
 
 /* Bits reported by sgm_plan_take_flags(): conditions on which the reference raises. */
@@ -80,6 +86,11 @@ typedef struct sgm_grid sgm_grid;
 int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam,
                    const int32_t* fam_m, const int64_t* fam_off, const double* fam_knots,
                    double tol, sgm_grid** out);
+/* Same numbering, with the knot vector of every (term, direction) named by a family index
+ * (-1 = single node at 0) instead of by its node count; families may have one knot. */
+int sgm_grid_build_families(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
+                            const int64_t* fam_off, const double* fam_knots, double tol,
+                            sgm_grid** out);
 int64_t sgm_grid_num_nodes(const sgm_grid* g);     /* M                                   */
 int64_t sgm_grid_map_size(const sgm_grid* g);      /* sum_t S_t                           */
 int64_t sgm_grid_nnz(const sgm_grid* g);           /* non-zero coordinates over all nodes */
@@ -115,6 +126,9 @@ typedef struct sgm_plan_desc {
     const int64_t* fam_off;    /* n_fam+1 offsets into fam_knots / fam_lambda               */
     const double* fam_knots;   /* knots of each family, ascending, >= 2 per family          */
     const double* fam_lambda;  /* barycentric lambda per knot (SGM_LAGRANGE only, else NULL) */
+    const int32_t* fam_newrank;/* SGM_HIER_PW_LINEAR only: per knot its rank among the knots
+                                  that are NEW on this level, -1 for knots of the coarser
+                                  level; term tables then have one entry per new-knot tuple */
 } sgm_plan_desc;
 
 typedef struct sgm_plan sgm_plan;
@@ -153,6 +167,13 @@ int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_p
                         const double* const* f, const int64_t* M, const int64_t* ldf,
                         int64_t NF, double* out, int64_t ldo,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* One batch of the dimension-wise hierarchisation used by SGM_HIER_PW_LINEAR plans:
+ *   alpha[child[i], :] -= wa[i] * alpha[pa[i], :] + wb[i] * alpha[pb[i], :]   (pb[i] < 0: one parent)
+ * for i < n; children of a batch are distinct and never parents of the same batch.
+ * alpha is M x ld (fp64, device), NF columns are updated. */
+int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, const int32_t* pa,
+                   const int32_t* pb, const double* wa, const double* wb, int64_t n, void* stream);
 
 /* W[p, :] = Levy-Ciesielski expansion of Brownian motion on [0, T] at times tt for the
  * parameter vector yy[p, 0:d]  (reference: param_LC_Brownian_motion,

@@ -33,7 +33,7 @@ class DevicePlan:
     """Packed tables of one interpolant resident on one GPU (sgm_plan)."""
 
     def __init__(self, kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
-                 device=None):
+                 device=None, fam_newrank=None):
         """term_fam: (T, N) knot-family index per direction, -1 where the term has one node;
         fam_off / fam_knots: CSR list of the families' ascending knot vectors."""
         torch = torch_cuda()
@@ -51,6 +51,8 @@ class DevicePlan:
         if kind == _lib.KIND_LAGRANGE:
             lam = np.concatenate([lagrange_lambdas(fam_knots[fam_off[i]:fam_off[i + 1]])
                                   for i in range(n_fam)]) if n_fam else np.zeros(0)
+        # (named so that it outlives the ctypes call below)
+        newrank = None if fam_newrank is None else np.ascontiguousarray(fam_newrank, dtype=np.int32)
         self.T = coeffs.shape[0]
         desc = _lib.PlanDesc(
             kind=self.kind, N=self.N, T=self.T, M=self.M,
@@ -58,7 +60,8 @@ class DevicePlan:
             map_off=_lib.ptr(map_off, _lib.c_i64), maps=_lib.ptr(maps, _lib.c_i32),
             n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
             fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
-            fam_lambda=_lib.ptr(lam, _lib.c_f64))
+            fam_lambda=_lib.ptr(lam, _lib.c_f64),
+            fam_newrank=_lib.ptr(newrank, _lib.c_i32))
         handle = _lib.c_vp()
         _lib.check(lib.sgm_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
         self._h = handle

@@ -21,6 +21,7 @@ SGM_OK = 0
 SGM_ERR_INVALID, SGM_ERR_CUDA, SGM_ERR_OVERFLOW, SGM_ERR_NODE_TOL, SGM_ERR_WORKSPACE = \
     -1, -2, -3, -4, -5
 KIND_LINEAR, KIND_QUADRATIC, KIND_CUBIC, KIND_LAGRANGE = 0, 1, 2, 3
+KIND_HIER_LINEAR = 5
 FLAG_QUADRATIC_RIGHT = 1
 
 c_i32, c_i64, c_f64, c_vp, c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
@@ -33,7 +34,7 @@ class PlanDesc(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("N", c_i32), ("T", c_i64), ("M", c_i64),
                 ("coeffs", p_f64), ("term_fam", p_i32), ("map_off", p_i64), ("maps", p_i32),
                 ("n_fam", c_i32), ("fam_off", p_i64), ("fam_knots", p_f64),
-                ("fam_lambda", p_f64)]
+                ("fam_lambda", p_f64), ("fam_newrank", p_i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sgm_b200.h
@@ -43,6 +44,10 @@ SIGNATURES = {
     "sgm_host_combination_coeffs": (ctypes.c_int, [p_i64, c_i64, c_i32, p_i64]),
     "sgm_grid_build": (ctypes.c_int, [c_i64, c_i32, p_i32, c_i32, p_i32, p_i64, p_f64, c_f64,
                                       ctypes.POINTER(c_vp)]),
+    "sgm_grid_build_families": (ctypes.c_int, [c_i64, c_i32, p_i32, c_i32, p_i64, p_f64, c_f64,
+                                               ctypes.POINTER(c_vp)]),
+    "sgm_hier_apply": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                      c_vp]),
     "sgm_grid_num_nodes": (c_i64, [c_vp]),
     "sgm_grid_map_size": (c_i64, [c_vp]),
     "sgm_grid_nnz": (c_i64, [c_vp]),
@@ -167,17 +172,26 @@ def combination_coeffs(mid_set):
 class HostGrid:
     """Owner of an sgm_grid handle (sparse-grid node numbering)."""
 
-    def __init__(self, num_nodes, fam_m, fam_off, fam_knots, tol=1.e-10):
+    def __init__(self, num_nodes, fam_m, fam_off, fam_knots, tol=1.e-10, term_fam=None):
+        """Either ``num_nodes`` (T, N) with the families keyed by node count ``fam_m``, or
+        ``term_fam`` (T, N) naming a family per (term, direction), -1 = single node at 0."""
         lib = load()
-        num_nodes = np.ascontiguousarray(num_nodes, dtype=np.int32)
-        self.T, self.N = num_nodes.shape
-        fam_m = np.ascontiguousarray(fam_m, dtype=np.int32)
         fam_off = np.ascontiguousarray(fam_off, dtype=np.int64)
         fam_knots = np.ascontiguousarray(fam_knots, dtype=np.float64)
         handle = c_vp()
-        check(lib.sgm_grid_build(self.T, self.N, ptr(num_nodes, c_i32), fam_m.size,
-                                 ptr(fam_m, c_i32), ptr(fam_off, c_i64), ptr(fam_knots, c_f64),
-                                 tol, ctypes.byref(handle)))
+        if term_fam is not None:
+            term_fam = np.ascontiguousarray(term_fam, dtype=np.int32)
+            self.T, self.N = term_fam.shape
+            check(lib.sgm_grid_build_families(self.T, self.N, ptr(term_fam, c_i32),
+                                              fam_off.size - 1, ptr(fam_off, c_i64),
+                                              ptr(fam_knots, c_f64), tol, ctypes.byref(handle)))
+        else:
+            num_nodes = np.ascontiguousarray(num_nodes, dtype=np.int32)
+            self.T, self.N = num_nodes.shape
+            fam_m = np.ascontiguousarray(fam_m, dtype=np.int32)
+            check(lib.sgm_grid_build(self.T, self.N, ptr(num_nodes, c_i32), fam_m.size,
+                                     ptr(fam_m, c_i32), ptr(fam_off, c_i64),
+                                     ptr(fam_knots, c_f64), tol, ctypes.byref(handle)))
         self._h = handle
         self.num_nodes = int(lib.sgm_grid_num_nodes(handle))
         self.map_size = int(lib.sgm_grid_map_size(handle))

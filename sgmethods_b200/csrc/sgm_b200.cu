@@ -73,6 +73,7 @@ int upload(sgm_plan* plan, const std::vector<T>& host, const T** dev_ptr) {
 
 int radix_of(int kind, int m) {
     switch (kind) {
+        case SGM_HIER_PW_LINEAR: return 1;
         case SGM_PW_LINEAR: return 2;
         case SGM_PW_QUADRATIC: return 3;
         case SGM_PW_CUBIC: return 4;
@@ -81,6 +82,7 @@ int radix_of(int kind, int m) {
 }
 int basis_width(int kind, int m) {
     switch (kind) {
+        case SGM_HIER_PW_LINEAR: return 1;  // value of the one non-zero hierarchical hat
         case SGM_PW_LINEAR: return 1;       // y; the lower weight 1 - y is formed on use
         case SGM_PW_QUADRATIC: return 3;
         case SGM_PW_CUBIC: return 4;
@@ -93,7 +95,7 @@ struct PointLaunch { int threads; size_t smem; bool global_basis; int blocks_per
 
 PointLaunch choose_point_launch(const sgm_plan* plan) {
     const PlanDev& d = plan->dev;
-    const size_t fixed = (size_t)d.n_knots * 8 * (d.kind == SGM_LAGRANGE ? 2 : 1);
+    const size_t fixed = (size_t)d.n_knots * 8 * (d.kind == SGM_LAGRANGE || d.kind == SGM_HIER_PW_LINEAR ? 2 : 1);
     const size_t per_point = (size_t)d.B * 8 + (size_t)d.E * 2;
     const size_t cap = (size_t)plan->max_smem_optin;
     const size_t per_sm = 228 * 1024;
@@ -140,7 +142,7 @@ SplitKernel split_kernel_for(int warps, int chunk) {
 template <int KIND>
 SplitLaunch choose_split_launch(const sgm_plan* plan) {
     const PlanDev& d = plan->dev;
-    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1) +
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) +
                          (size_t)d.B * 32 * 8 + (size_t)d.E * 32 * 2 + 32 * 8 + 64;
     SplitLaunch best{0, 0, 0, 0};
     int best_warps = 0;
@@ -238,7 +240,7 @@ int launch_cols_cpl(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, con
                     int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
                     int accumulate, cudaStream_t stream) {
     const PlanDev& d = plan->dev;
-    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1);
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
     const size_t per_warp = (size_t)d.B * 8 + (size_t)d.E * 4;
     int warps = 8;
     while (warps > 1 && fixed + per_warp * warps > (size_t)plan->max_smem_optin) warps >>= 1;
@@ -262,7 +264,7 @@ int launch_cols_wide(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, co
                      int64_t ldf, int64_t n_tiles, double* out, int64_t ldo, double scale,
                      int accumulate, cudaStream_t stream) {
     const PlanDev& d = plan->dev;
-    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1);
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
     const size_t per_warp = (size_t)d.B * 8 + (size_t)d.E * 4;
     int warps = 8;
     while (warps > 1 && fixed + per_warp * warps > (size_t)plan->max_smem_optin) warps >>= 1;
@@ -348,6 +350,7 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
                 return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             case SGM_PW_QUADRATIC: return launch_points_split<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             case SGM_PW_CUBIC: return launch_points_split<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_HIER_PW_LINEAR: return launch_points_split<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
             default: return launch_points_split<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
         }
     }
@@ -355,6 +358,7 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
         case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
         case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+        case SGM_HIER_PW_LINEAR: return launch_cols<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
         default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
     }
 }
@@ -369,8 +373,11 @@ int sgm_version(void) { return 100; }
 int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     if (!out) return sgm_fail(SGM_ERR_INVALID, "plan_create: null output");
     *out = nullptr;
-    if (!desc || desc->N <= 0 || desc->T < 0 || desc->kind < 0 || desc->kind > 3)
+    if (!desc || desc->N <= 0 || desc->T < 0 || desc->kind < 0 ||
+        (desc->kind > 3 && desc->kind != SGM_HIER_PW_LINEAR))
         return sgm_fail(SGM_ERR_INVALID, "plan_create: bad descriptor");
+    if (desc->kind == SGM_HIER_PW_LINEAR && desc->n_fam > 0 && !desc->fam_newrank)
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: hierarchical plan without new-knot ranks");
     if (desc->T > 0 && (!desc->coeffs || !desc->term_fam || !desc->map_off || !desc->maps))
         return sgm_fail(SGM_ERR_INVALID, "plan_create: null table");
     if (desc->T > 0x7fffffff) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: too many terms");
@@ -389,6 +396,26 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     const int64_t n_knots = desc->n_fam ? desc->fam_off[desc->n_fam] : 0;
     if (n_knots > 0x3fffffff) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: knot table too large");
 
+    // entries of a term table per direction: all knots, or (hierarchical form) the new knots
+    std::vector<int> fam_extent(std::max(desc->n_fam, 1), 0);
+    for (int f = 0; f < desc->n_fam; ++f) {
+        const int m = (int)(desc->fam_off[f + 1] - desc->fam_off[f]);
+        if (kind == SGM_HIER_PW_LINEAR) {
+            int n_new = 0;
+            for (int i = 0; i < m; ++i) {
+                const int r = desc->fam_newrank[desc->fam_off[f] + i];
+                if (r >= 0) { if (r != n_new) return sgm_fail(SGM_ERR_INVALID, "plan_create: new-knot ranks must count up"); ++n_new; }
+            }
+            for (int i = 0; i + 1 < m; ++i) {
+                const bool a = desc->fam_newrank[desc->fam_off[f] + i] >= 0;
+                const bool b = desc->fam_newrank[desc->fam_off[f] + i + 1] >= 0;
+                if (a == b) return sgm_fail(SGM_ERR_INVALID, "plan_create: every bracket needs exactly one new knot");
+            }
+            fam_extent[f] = n_new;
+        } else {
+            fam_extent[f] = m;
+        }
+    }
     // entries = distinct (direction, family) pairs in order of first use
     std::vector<int> entry_of((size_t)N * std::max(desc->n_fam, 1), -1);
     std::vector<Entry> entries;
@@ -419,7 +446,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
                 B += basis_width(kind, m);
             }
             tdim.push_back(TermDim{entries[e].boff, 0, radix_of(kind, m), e});
-            check *= m;
+            check *= fam_extent[fam];
             ncorner *= radix_of(kind, m);
             if (ncorner > 0x3fffffff || check > 0x7fffffff)
                 return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: term with more than 2^30 corner contributions");
@@ -430,7 +457,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         for (int j = h.k - 1; j >= 0; --j) {
             TermDim& d = tdim[h.dim_off + j];
             d.stride = stride;
-            stride *= entries[d.ent].n;
+            stride *= fam_extent[desc->term_fam[t * N + entries[d.ent].dim]];
         }
         h.ncorner = (int)ncorner;
         hdr[t] = h;
@@ -439,7 +466,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         r.coeff = desc->coeffs[t];
         r.val_off = h.val_off;
         r.info = h.k & 0xff;
-        bool packable = h.k <= 4 && (h.k == 0 || tdim[h.dim_off + h.k - 1].stride == 1);
+        bool packable = (kind == SGM_PW_LINEAR || kind == SGM_HIER_PW_LINEAR) && h.k <= 4 &&
+                        (h.k == 0 || tdim[h.dim_off + h.k - 1].stride == 1);
         for (int j = 0; j < h.k && packable; ++j) {
             const TermDim& d = tdim[h.dim_off + j];
             if (d.ent > 0xffff || d.stride > 0xffff) { packable = false; break; }
@@ -510,6 +538,9 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     } else {
         d.n_corners = 0;
     }
+    std::vector<short> newrank;
+    if (kind == SGM_HIER_PW_LINEAR)
+        for (int64_t i = 0; i < n_knots; ++i) newrank.push_back((short)desc->fam_newrank[i]);
     std::vector<unsigned> flags(4, 0u);
     int rc = SGM_OK;
     const unsigned* cflags = nullptr;
@@ -519,7 +550,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         (rc = upload(plan, maps, &d.maps)) ||
         (rc = upload(plan, corner_term, &d.corner_term)) ||
         (rc = upload(plan, corner_off, &d.corner_off)) || (rc = upload(plan, knots, &d.knots)) ||
-        (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, flags, &cflags))) {
+        (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, newrank, &d.newrank)) || (rc = upload(plan, flags, &cflags))) {
         sgm_plan_destroy(plan);
         return rc;
     }
@@ -583,6 +614,20 @@ int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_p
                           workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
     }
+    return SGM_OK;
+}
+
+int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, const int32_t* pa,
+                   const int32_t* pb, const double* wa, const double* wb, int64_t n, void* stream) {
+    if (n < 0 || NF < 1 || ld < NF) return sgm_fail(SGM_ERR_INVALID, "hier_apply: bad shapes");
+    if (n == 0) return SGM_OK;
+    if (!alpha || !child || !pa || !pb || !wa || !wb)
+        return sgm_fail(SGM_ERR_INVALID, "hier_apply: null buffer");
+    const int64_t total = n * NF;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    sgm::hier_apply_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        alpha, NF, ld, child, pa, pb, wa, wb, n);
+    SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }
 

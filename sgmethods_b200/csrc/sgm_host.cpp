@@ -198,23 +198,10 @@ int sgm_host_combination_coeffs(const int64_t* mid_set, int64_t card, int32_t N,
     return SGM_OK;
 }
 
-int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam,
-                   const int32_t* fam_m, const int64_t* fam_off, const double* fam_knots,
-                   double tol, sgm_grid** out) {
-    if (!out) return sgm_fail(SGM_ERR_INVALID, "grid_build: null output");
-    *out = nullptr;
-    if (T < 0 || N <= 0 || (T > 0 && !num_nodes) || n_fam < 0)
-        return sgm_fail(SGM_ERR_INVALID, "grid_build: bad sizes");
-    // family lookup by node count
-    int32_t max_m = 1;
-    for (int32_t f = 0; f < n_fam; ++f) {
-        if (fam_m[f] < 2 || fam_off[f + 1] - fam_off[f] != fam_m[f])
-            return sgm_fail(SGM_ERR_INVALID, "grid_build: family table inconsistent");
-        max_m = std::max(max_m, fam_m[f]);
-    }
-    std::vector<int32_t> fam_of_m(max_m + 1, -1);
-    for (int32_t f = 0; f < n_fam; ++f) fam_of_m[fam_m[f]] = f;
-
+// Shared implementation: every (term, direction) names a knot family (-1 = single node at 0).
+static int grid_build_impl(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
+                           const int64_t* fam_off, const double* fam_knots, double tol,
+                           sgm_grid** out) {
     // 1-D coordinate clusters (knots of every family and the 0.0 of inactive directions)
     std::vector<double> pool(fam_knots, fam_knots + (n_fam ? fam_off[n_fam] : 0));
     for (double v : pool)
@@ -237,12 +224,12 @@ int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam
     for (int64_t t = 0; t < T; ++t) {
         int64_t S = 1;
         for (int32_t n = 0; n < N; ++n) {
-            int32_t m = num_nodes[t * N + n];
-            if (m < 1 || (m > 1 && (m > max_m || fam_of_m[m] < 0))) {
+            const int32_t f = term_fam[t * N + n];
+            if (f >= n_fam) {
                 delete g;
-                return sgm_fail(SGM_ERR_INVALID, "grid_build: node count without knot family");
+                return sgm_fail(SGM_ERR_INVALID, "grid_build: knot family index out of range");
             }
-            S *= m;
+            if (f >= 0) S *= fam_off[f + 1] - fam_off[f];
             if (S > (int64_t)1 << 40) {
                 delete g;
                 return sgm_fail(SGM_ERR_OVERFLOW, "grid_build: tensor grid too large");
@@ -265,8 +252,12 @@ int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam
     for (int64_t t = 0; t < T; ++t) {
         adims.clear(); asize.clear(); afam.clear();
         for (int32_t n = 0; n < N; ++n) {
-            int32_t m = num_nodes[t * N + n];
-            if (m > 1) { adims.push_back(n); asize.push_back(m); afam.push_back(fam_of_m[m]); }
+            const int32_t f = term_fam[t * N + n];
+            if (f >= 0) {
+                adims.push_back(n);
+                asize.push_back((int32_t)(fam_off[f + 1] - fam_off[f]));
+                afam.push_back(f);
+            }
         }
         const int k = (int)adims.size();
         digit.assign(k, 0);
@@ -315,6 +306,45 @@ int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam
     }
     *out = g;
     return SGM_OK;
+}
+
+int sgm_grid_build(int64_t T, int32_t N, const int32_t* num_nodes, int32_t n_fam,
+                   const int32_t* fam_m, const int64_t* fam_off, const double* fam_knots,
+                   double tol, sgm_grid** out) {
+    if (!out) return sgm_fail(SGM_ERR_INVALID, "grid_build: null output");
+    *out = nullptr;
+    if (T < 0 || N <= 0 || (T > 0 && !num_nodes) || n_fam < 0)
+        return sgm_fail(SGM_ERR_INVALID, "grid_build: bad sizes");
+    // family lookup by node count
+    int32_t max_m = 1;
+    for (int32_t f = 0; f < n_fam; ++f) {
+        if (fam_m[f] < 2 || fam_off[f + 1] - fam_off[f] != fam_m[f])
+            return sgm_fail(SGM_ERR_INVALID, "grid_build: family table inconsistent");
+        max_m = std::max(max_m, fam_m[f]);
+    }
+    std::vector<int32_t> fam_of_m(max_m + 1, -1);
+    for (int32_t f = 0; f < n_fam; ++f) fam_of_m[fam_m[f]] = f;
+    std::vector<int32_t> term_fam((size_t)T * N, -1);
+    for (int64_t i = 0; i < T * N; ++i) {
+        const int32_t m = num_nodes[i];
+        if (m < 1 || (m > 1 && (m > max_m || fam_of_m[m] < 0)))
+            return sgm_fail(SGM_ERR_INVALID, "grid_build: node count without knot family");
+        term_fam[i] = m > 1 ? fam_of_m[m] : -1;
+    }
+    return grid_build_impl(T, N, term_fam.data(), n_fam, fam_off, fam_knots, tol, out);
+}
+
+int sgm_grid_build_families(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
+                            const int64_t* fam_off, const double* fam_knots, double tol,
+                            sgm_grid** out) {
+    if (!out) return sgm_fail(SGM_ERR_INVALID, "grid_build: null output");
+    *out = nullptr;
+    if (T < 0 || N <= 0 || (T > 0 && !term_fam) || n_fam < 0 || (n_fam > 0 && (!fam_off || !fam_knots)))
+        return sgm_fail(SGM_ERR_INVALID, "grid_build: bad sizes");
+    for (int32_t f = 0; f < n_fam; ++f)
+        if (fam_off[f + 1] - fam_off[f] < 1)
+            return sgm_fail(SGM_ERR_INVALID, "grid_build: empty knot family");
+    return grid_build_impl(T, N, term_fam, n_fam, fam_off, fam_knots, tol, out);
 }
 
 int64_t sgm_grid_num_nodes(const sgm_grid* g) { return g ? g->M : 0; }

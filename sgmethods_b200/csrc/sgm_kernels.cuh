@@ -44,6 +44,10 @@ constexpr int SGM_LINEAR_WIDE = 4;
 __host__ __device__ constexpr int base_kind(int kind) {
     return kind == SGM_LINEAR_WIDE ? (int)SGM_PW_LINEAR : kind;
 }
+// corner contributions per active direction for the fixed-radix kinds
+__host__ __device__ constexpr int fixed_radix(int kind) {
+    return kind == SGM_HIER_PW_LINEAR ? 1 : (base_kind(kind) == SGM_PW_LINEAR ? 2 : (kind == SGM_PW_QUADRATIC ? 3 : 4));
+}
 
 // Device view of a plan (passed by value to the kernels).
 struct PlanDev {
@@ -61,6 +65,7 @@ struct PlanDev {
     int n_corners;                     // sum_t C_t (0 if the list is not built)
     const double* knots;
     const double* lambda;
+    const short* newrank;              // SGM_HIER_PW_LINEAR: rank of a knot among the new knots, -1 old
     unsigned* flags;
     // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
     // coarsest knot family used in that direction), for the n_key most used directions
@@ -96,7 +101,18 @@ __device__ __forceinline__ void fill_basis(const Entry e, double x, const double
     const double* g = knots + e.knot_off;
     const int n = e.n;
     double* b = bas + (size_t)e.boff * bs;
-    if (base_kind(KIND) == SGM_PW_LINEAR) {
+    if (KIND == SGM_HIER_PW_LINEAR) {
+        // bracket as for pw-linear; exactly one end of the bracket is a knot that is new on
+        // this level: its hat value at x is the only non-zero hierarchical basis function
+        // (`lambda` carries the new-knot ranks of this plan kind, stored as doubles' bits)
+        const short* nr = reinterpret_cast<const short*>(lambda) + e.knot_off;
+        int i = count_le(g, n, x) - 1;
+        i = max(0, min(i, n - 2));
+        const double y = (x - g[i]) / (g[i + 1] - g[i]);
+        const int r_lo = nr[i];
+        b[0] = r_lo >= 0 ? 1.0 - y : y;
+        idx[(size_t)ent_id * bs] = (IdxT)(r_lo >= 0 ? r_lo : nr[i + 1]);
+    } else if (base_kind(KIND) == SGM_PW_LINEAR) {
         int i = count_le(g, n, x) - 1;
         i = max(0, min(i, n - 2));
         b[0] = (x - g[i]) / (g[i + 1] - g[i]);
@@ -273,9 +289,10 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
     for (int i = tid; i < pl.n_knots; i += bs) {
         sknots[i] = pl.knots[i];
         if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
     }
     unsigned char* after = reinterpret_cast<unsigned char*>(
-        sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots);
+        sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots);
     double* bas;
     unsigned short* idx;
     if (GLOBAL_BASIS) {
@@ -373,6 +390,23 @@ __device__ __forceinline__ double linear_term_packed(const int4 r1, const double
     return tp;
 }
 
+// hierarchical-surplus term: ONE table entry per term, weight = ((1*phi_0)*phi_1)*...
+template <int K>
+__device__ __forceinline__ double hier_term_packed(const int4 r1, const double* bas,
+                                                   const unsigned short* idx,
+                                                   const double* __restrict__ At) {
+    double w = 1.0;
+    unsigned off = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const unsigned e = (unsigned)((j < 2 ? r1.x : r1.y) >> (16 * (j & 1))) & 0xffffu;
+        const unsigned sd = (unsigned)((j < 2 ? r1.z : r1.w) >> (16 * (j & 1))) & 0xffffu;
+        w = w * bas[e * 32];
+        off += (unsigned)idx[e * 32] * sd;
+    }
+    return At[off] * w;
+}
+
 template <int KIND, int W, int CHUNK>
 __global__ void __launch_bounds__(W * 32)
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
@@ -388,8 +422,9 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
         if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
     }
-    double* bas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* bas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* sP = bas_all + (size_t)pl.B * 32;                 // [2][chunk][32]
     double* sOut = sP + 2 * (size_t)chunk * 32;               // [32]
     unsigned short* idx_all = reinterpret_cast<unsigned short*>(sOut + 32);
@@ -433,6 +468,15 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                         case 2: tp = linear_term_packed<2>(r1, bas, idx, G + r0.z); break;
                         case 3: tp = linear_term_packed<3>(r1, bas, idx, G + r0.z); break;
                         default: tp = linear_term_packed<4>(r1, bas, idx, G + r0.z); break;
+                    }
+                } else if (KIND == SGM_HIER_PW_LINEAR && (r0.w & TERMREC_PACKED)) {
+                    const int4 r1 = __ldg(rec4 + 2 * t + 1);
+                    switch (r0.w & 0xff) {
+                        case 0: tp = G[r0.z]; break;
+                        case 1: tp = hier_term_packed<1>(r1, bas, idx, G + r0.z); break;
+                        case 2: tp = hier_term_packed<2>(r1, bas, idx, G + r0.z); break;
+                        case 3: tp = hier_term_packed<3>(r1, bas, idx, G + r0.z); break;
+                        default: tp = hier_term_packed<4>(r1, bas, idx, G + r0.z); break;
                     }
                 } else {
                     const TermHdr h = pl.hdr[t];
@@ -541,8 +585,9 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
         if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
     }
-    double* sbas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* bas = sbas_all + (size_t)warp * pl.B;
     int* idx = reinterpret_cast<int*>(sbas_all + (size_t)n_warps * pl.B) + (size_t)warp * pl.E;
     __syncthreads();
@@ -595,7 +640,7 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
                         } else {
                             // fixed radix 2 / 3 / 4: digits by constant division, most
                             // significant digit = first active direction
-                            constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
+                            constexpr int R = fixed_radix(KIND);
                             int cs = h.ncorner;
                             int rem = cid;
                             for (int j = 0; j < h.k; ++j) {
@@ -660,8 +705,9 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
         if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
     }
-    double* sbas_all = sknots + (KIND == SGM_LAGRANGE ? 2 : 1) * (size_t)pl.n_knots;
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* bas = sbas_all + (size_t)warp * pl.B;
     int* idx = reinterpret_cast<int*>(sbas_all + (size_t)n_warps * pl.B) + (size_t)warp * pl.E;
     __syncthreads();
@@ -709,7 +755,7 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
                         off += (idx[d.ent] + a) * d.stride;
                     }
                 } else {
-                    constexpr int R = KIND == SGM_PW_LINEAR ? 2 : (KIND == SGM_PW_QUADRATIC ? 3 : 4);
+                    constexpr int R = fixed_radix(KIND);
                     int cs = h.ncorner;
                     int rem = cid;
                     for (int j = 0; j < h.k; ++j) {
@@ -763,6 +809,21 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
             }
             *dst = r;
         }
+    }
+}
+
+// One batch of the dimension-wise hierarchisation (surplus = value - coarser interpolant).
+__global__ void hier_apply_kernel(double* __restrict__ alpha, int64_t NF, int64_t ld,
+                                  const int* __restrict__ child, const int* __restrict__ pa,
+                                  const int* __restrict__ pb, const double* __restrict__ wa,
+                                  const double* __restrict__ wb, int64_t n) {
+    const int64_t total = n * NF;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t it = i / NF, c = i - it * NF;
+        double coarse = wa[it] * alpha[(int64_t)pa[it] * ld + c];
+        if (pb[it] >= 0) coarse = coarse + wb[it] * alpha[(int64_t)pb[it] * ld + c];
+        alpha[(int64_t)child[it] * ld + c] -= coarse;
     }
 }
 

@@ -491,3 +491,58 @@ def test_levy_ciesielski_many_levels_uses_generic_kernel():
     yy = rng.normal(size=(3, 5000))                 # L = 13 > 12
     W = param_LC_Brownian_motion(tt, yy, 1.0)
     assert np.array_equal(W[1], brownian_oracle.lc_brownian(tt, yy[1], 1.0))
+
+
+# ------------------------------------------------------- opt-in hierarchical-surplus form
+@pytest.mark.parametrize("NF", [1, 3, 200])
+def test_hierarchical_form_agrees_with_combination_formula(NF):
+    """Not bit-identical by design (different but equivalent formula); 1e-10 of max|ref| here,
+    and at least as close to a long-double evaluation as the float64 combination formula."""
+    rng = np.random.default_rng(21)
+    it = SGInterpolant(mis.smolyak_mid_set(4, 6), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    x = rng.normal(0, 1.5, (500, 6))
+    f = rng.normal(size=(it.num_nodes, NF))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x, f, squeeze=False)
+    got = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(ref.shape)
+    assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    exact = np.asarray(it.interpolate(x, f)).reshape(ref.shape)
+    assert np.array_equal(exact, ref)                        # the default stays bit-identical
+    with pytest.raises(ValueError):
+        it.interpolate(x, f, method="fast")
+
+
+def test_hierarchical_form_smooth_function_vs_long_double():
+    S = mis.smolyak_mid_set(4, 8)
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+    w = 1.0 / np.arange(1, 9) ** 2
+    f = np.sin(it.SG @ w).reshape(-1, 1)
+    x = np.random.default_rng(0).normal(size=(300, 8))
+    plan = oracle_plan_of(it)
+    # long-double evaluation of the combination formula (same algorithm, 64-bit mantissa)
+    truth = np.zeros(300, dtype=np.longdouble)
+    for c, dims, nodes, tmap in zip(plan.coeffs, plan.dims, plan.nodes, plan.maps):
+        vals = f[tmap, 0].astype(np.longdouble)
+        if dims.size == 0:
+            truth += np.longdouble(c) * vals.reshape(-1)[0]
+            continue
+        acc = np.zeros(300, dtype=np.longdouble)
+        lo, wy = [], []
+        for j, d in enumerate(dims):
+            g = np.asarray(nodes[j], dtype=np.longdouble)
+            i = np.clip(np.searchsorted(nodes[j], x[:, d], side="right") - 1, 0, g.size - 2)
+            lo.append(i)
+            wy.append((x[:, d].astype(np.longdouble) - g[i]) / (g[i + 1] - g[i]))
+        from itertools import product
+        for corner in product((0, 1), repeat=dims.size):
+            wgt = np.ones(300, dtype=np.longdouble)
+            for j, b in enumerate(corner):
+                wgt = wgt * (wy[j] if b else 1 - wy[j])
+            acc = acc + vals[tuple(lo[j] + corner[j] for j in range(dims.size))] * wgt
+        truth += np.longdouble(c) * acc
+    exact = it.interpolate(x, f)
+    fast = it.interpolate(x, f, method="hierarchical")
+    err_exact = float(np.max(np.abs(exact - truth)))
+    err_fast = float(np.max(np.abs(fast - truth)))
+    print(f"float64 combination formula err {err_exact:.2e}, hierarchical form err {err_fast:.2e}")
+    assert err_fast <= max(err_exact, 1e-15) * 1.5

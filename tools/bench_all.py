@@ -68,6 +68,43 @@ for w in which:
     elif w == "c2":
         it = SGInterpolant(mis.smolyak_mid_set(4, 16), nodes_1d.unbounded_nodes_nested, l2, verbose=False)
         run_interp("c2 d=16 w=4 pw-linear", it, 10 ** 6, 1)
+    elif w == "c2hier":
+        it = SGInterpolant(mis.smolyak_mid_set(4, 16), nodes_1d.unbounded_nodes_nested, l2, verbose=False)
+        t1 = time.time(); hp = it.hierarchical(); t_build = time.time() - t1
+        gen = torch.Generator(device=dev).manual_seed(0)
+        P = 10 ** 6
+        x = torch.randn((P, 16), dtype=torch.float64, device=dev, generator=gen)
+        f = torch.randn((it.num_nodes, 1), dtype=torch.float64, device=dev, generator=gen)
+        exact = it.interpolate(x, f)
+        fast = hp.interpolate(x, f)
+        dev_rel = float((fast - exact).abs().max() / exact.abs().max())
+        ms_all = timed(lambda: hp.interpolate(x, f))
+        alpha = hp.surpluses(f)
+        plan = hp._dev(0)[0]
+        out = torch.empty((P, 1), dtype=torch.float64, device=dev)
+        ms_eval = timed(lambda: plan.eval(x, alpha, out))
+        print(json.dumps({"case": "c2 hierarchical-surplus form (opt-in)", "P": P, "host_build_s": t_build,
+                          "ms_total": ms_all, "ms_eval_only": ms_eval, "evals_per_s": P / ms_all * 1e3,
+                          "max_rel_dev_from_exact_path": dev_rel}), flush=True)
+    elif w == "c3hier":
+        a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
+        it = SGInterpolant(mis.aniso_smolyak_mid_set(10, 64, a),
+                           lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2), l2, verbose=False)
+        t1 = time.time(); hp = it.hierarchical(); t_build = time.time() - t1
+        gen = torch.Generator(device=dev).manual_seed(0)
+        P, NF = 10 ** 4, 10 ** 4
+        x = torch.randn((P, 64), dtype=torch.float64, device=dev, generator=gen)
+        f = torch.randn((it.num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
+        exact = it.interpolate(x, f)
+        fast = hp.interpolate(x, f)
+        dev_rel = float((fast - exact).abs().max() / exact.abs().max())
+        ms_exact = timed(lambda: it.interpolate(x, f), 3)
+        ms_all = timed(lambda: hp.interpolate(x, f), 3)
+        ms_hier = timed(lambda: hp.surpluses(f), 3)
+        print(json.dumps({"case": "c3 (w=10) hierarchical-surplus form (opt-in)", "P": P, "NF": NF,
+                          "host_build_s": t_build, "ms_exact": ms_exact, "ms_total": ms_all,
+                          "ms_hierarchisation": ms_hier, "evals_per_s": P * NF / ms_all * 1e3,
+                          "max_rel_dev_from_exact_path": dev_rel}), flush=True)
     elif w == "c3":
         a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
         for wlev, P, NF in ((8, 10 ** 4, 10 ** 4), (10, 10 ** 4, 10 ** 4)):
