@@ -643,18 +643,19 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
     SGM_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (L <= 12 && nt >= 32) {
+    const size_t lc_smem = (size_t)sgm::LC_ROWS * d * 8;
+    if (L <= 12 && nt >= 32 && lc_smem <= 48 * 1024) {
         const int tpt = L <= 6 ? 4 : 2;
         const int64_t gx = (nt + 256 * tpt - 1) / (256 * tpt);
         // enough blocks to fill the GPU several times over, at least 8 rows per block
-        int64_t rows = std::max<int64_t>(8, (P * gx + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16));
+        int64_t rows = std::max<int64_t>(sgm::LC_ROWS, (P * gx + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16));
         int64_t gy = (P + rows - 1) / rows;
         if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
         if (L <= 6)
-            sgm::lc_brownian_tiles_kernel<6, 4><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(
+            sgm::lc_brownian_tiles_kernel<6, 4><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
                 tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
         else
-            sgm::lc_brownian_tiles_kernel<12, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(
+            sgm::lc_brownian_tiles_kernel<12, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
                 tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
     } else {
         const int64_t total = P * nt;

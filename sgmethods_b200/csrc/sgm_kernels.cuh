@@ -868,6 +868,7 @@ __global__ void lc_brownian_kernel(const double* __restrict__ tt, int64_t nt,
 // (they do not depend on the parameter vector) and then streams over the rows: per output
 // L x (load y_k, two multiplies, one add) and one store; a block writes 2*TPT KB of every row
 // contiguously, which keeps the HBM write stream page-friendly.
+constexpr int LC_ROWS = 32;
 template <int LMAX, int TPT>
 __global__ void __launch_bounds__(256)
 lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
@@ -907,24 +908,32 @@ lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
             }
         }
     }
+    // rows are staged 32 at a time in shared memory (coalesced copy) so that the per-level
+    // coefficient reads are shared-memory broadcasts instead of L2 round trips
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sy = reinterpret_cast<double*>(smem_raw);          // [LC_ROWS][d]
     const int64_t p0 = (int64_t)blockIdx.y * rows_per_block;
     const int64_t p1 = min(P, p0 + rows_per_block);
-    for (int64_t p = p0; p < p1; ++p) {
-        const double* y = yy + p * ldy;
-        const double y0 = __ldg(y);
-        double* wrow = W + p * ldw;
-        double yk[TPT][LMAX];
+    for (int64_t pb = p0; pb < p1; pb += LC_ROWS) {
+        const int nrows = (int)min((int64_t)LC_ROWS, p1 - pb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nrows * d; i += 256) {
+            const int r = i / d, c = i - r * d;
+            sy[i] = __ldg(yy + (pb + r) * ldy + c);
+        }
+        __syncthreads();
+        for (int r = 0; r < nrows; ++r) {
+            const double* y = sy + (size_t)r * d;
+            const double y0 = y[0];
+            double* wrow = W + (pb + r) * ldw;
 #pragma unroll
-        for (int q = 0; q < TPT; ++q)
+            for (int q = 0; q < TPT; ++q) {
+                double w = y0 * sv[q];
 #pragma unroll
-            for (int l = 0; l < LMAX; ++l) yk[q][l] = __ldg(y + kidx[q][l]);
-#pragma unroll
-        for (int q = 0; q < TPT; ++q) {
-            double w = y0 * sv[q];
-#pragma unroll
-            for (int l = 0; l < LMAX; ++l) w = w + (yk[q][l] * scl[l]) * eta[q][l];
-            const int64_t it = t_base + q * 256;
-            if (it < nt) wrow[it] = w * sqrtT;
+                for (int l = 0; l < LMAX; ++l) w = w + (y[kidx[q][l]] * scl[l]) * eta[q][l];
+                const int64_t it = t_base + q * 256;
+                if (it < nt) wrow[it] = w * sqrtT;
+            }
         }
     }
 }
