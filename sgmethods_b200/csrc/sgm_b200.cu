@@ -49,6 +49,7 @@ struct sgm_plan {
     PlanDev dev{};
     int64_t n_vals = 0;          // sum_t S_t
     int64_t corners = 0;         // sum_t C_t
+    bool all_packed = false;     // every term has a packed record (needed by the H1 kernel)
     int64_t table_bytes = 0;
     int kmax = 0;
     int sm_count = 148;
@@ -181,7 +182,7 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
         return launch_points<KIND>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
-    const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+    int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
     // locality sort of the points (scratch: perm P ints | keys P u16 | 65536 bins)
     const int* perm = nullptr;
     const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
@@ -200,6 +201,25 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
         sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, perm_w);
         SGM_CUDA(cudaGetLastError());
         perm = perm_w;
+    }
+    if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !std::getenv("SGM_NO_H1")) {
+        constexpr int HW = 16;
+        const PlanDev& d = plan->dev;
+        const size_t smem = (size_t)d.n_knots * 16 + (size_t)d.B * 32 * 8 + (size_t)HW * 32 * 8 +
+                            (size_t)d.E * 32 * 2 + 64;
+        auto hk = sgm::eval_hier_points_kernel<HW>;
+        if (smem <= (size_t)plan->max_smem_optin &&
+            cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+            int bps = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, hk, HW * 32, smem);
+            if (bps >= 1) {
+                blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * bps);
+                hk<<<(unsigned)blocks, HW * 32, smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo, scale,
+                                                            accumulate, perm);
+                SGM_CUDA(cudaGetLastError());
+                return SGM_OK;
+            }
+        }
     }
     SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk);
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
@@ -421,6 +441,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     std::vector<Entry> entries;
     std::vector<TermHdr> hdr((size_t)T);
     std::vector<TermRec> rec((size_t)T);
+    int64_t n_packed = 0;
     std::vector<TermDim> tdim;
     int B = 0;
     int64_t corners = 0;
@@ -453,11 +474,20 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
             ++h.k;
         }
         if (check != S) return sgm_fail(SGM_ERR_INVALID, "plan_create: map size does not match node counts");
-        int stride = 1;                                    // C order: last active direction fastest
-        for (int j = h.k - 1; j >= 0; --j) {
-            TermDim& d = tdim[h.dim_off + j];
-            d.stride = stride;
-            stride *= fam_extent[desc->term_fam[t * N + entries[d.ent].dim]];
+        if (kind == SGM_HIER_PW_LINEAR) {
+            int stride = 1;                                // surplus tables: FIRST direction fastest
+            for (int j = 0; j < h.k; ++j) {
+                TermDim& d = tdim[h.dim_off + j];
+                d.stride = stride;
+                stride *= fam_extent[desc->term_fam[t * N + entries[d.ent].dim]];
+            }
+        } else {
+            int stride = 1;                                // C order: last active direction fastest
+            for (int j = h.k - 1; j >= 0; --j) {
+                TermDim& d = tdim[h.dim_off + j];
+                d.stride = stride;
+                stride *= fam_extent[desc->term_fam[t * N + entries[d.ent].dim]];
+            }
         }
         h.ncorner = (int)ncorner;
         hdr[t] = h;
@@ -467,7 +497,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         r.val_off = h.val_off;
         r.info = h.k & 0xff;
         bool packable = (kind == SGM_PW_LINEAR || kind == SGM_HIER_PW_LINEAR) && h.k <= 4 &&
-                        (h.k == 0 || tdim[h.dim_off + h.k - 1].stride == 1);
+                        (h.k == 0 || kind == SGM_HIER_PW_LINEAR || tdim[h.dim_off + h.k - 1].stride == 1);
+        if (packable) ++n_packed;
         for (int j = 0; j < h.k && packable; ++j) {
             const TermDim& d = tdim[h.dim_off + j];
             if (d.ent > 0xffff || d.stride > 0xffff) { packable = false; break; }
@@ -477,6 +508,16 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         if (packable) r.info |= sgm::TERMREC_PACKED;
         corners += ncorner;
         kmax = std::max(kmax, h.k);
+    }
+    // common prefix (leading (direction, family) entries) with the previous term, bits 12..14
+    for (int64_t t = 1; t < T; ++t) {
+        TermRec& r = rec[t];
+        const TermRec& q = rec[t - 1];
+        if (!(r.info & sgm::TERMREC_PACKED) || !(q.info & sgm::TERMREC_PACKED)) continue;
+        const int kk = std::min(r.info & 0xff, q.info & 0xff);
+        int cp = 0;
+        while (cp < kk && cp < 3 && r.ent[cp] == q.ent[cp]) ++cp;
+        r.info |= cp << 12;
     }
     for (int64_t i = 0; i < desc->map_off[T]; ++i)
         if (desc->maps[i] < 0 || desc->maps[i] >= desc->M)
@@ -492,6 +533,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     plan->n_vals = desc->map_off[T];
     plan->corners = corners;
+    plan->all_packed = (n_packed == T);
     plan->kmax = kmax;
     PlanDev& d = plan->dev;
     d.kind = kind; d.N = N; d.E = (int)entries.size(); d.B = B; d.T = (int)T;
@@ -645,14 +687,14 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t lc_smem = (size_t)sgm::LC_ROWS * d * 8;
     if (L <= 12 && nt >= 32 && lc_smem <= 48 * 1024) {
-        const int tpt = L <= 6 ? 4 : 2;
+        const int tpt = 2;
         const int64_t gx = (nt + 256 * tpt - 1) / (256 * tpt);
         // enough blocks to fill the GPU several times over, at least 8 rows per block
         int64_t rows = std::max<int64_t>(sgm::LC_ROWS, (P * gx + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16));
         int64_t gy = (P + rows - 1) / rows;
         if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
         if (L <= 6)
-            sgm::lc_brownian_tiles_kernel<6, 4><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
+            sgm::lc_brownian_tiles_kernel<6, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
                 tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
         else
             sgm::lc_brownian_tiles_kernel<12, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(

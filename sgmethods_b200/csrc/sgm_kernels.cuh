@@ -504,6 +504,118 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel H1: dedicated scalar kernel of the opt-in hierarchical-surplus form.  Block = 32
+// points x W warps; every warp takes a contiguous range of the (lexicographically sorted)
+// multi-indices and keeps the running weight / offset prefixes of the leading directions in
+// registers: consecutive multi-indices share all but their last active direction, so a
+// term costs two shared-memory reads, one multiply, one table gather and one FMA.  Term
+// tables are laid out with the FIRST active direction fastest, which makes the offset prefix
+// reusable.  Partial sums of the W warps are added in warp order (deterministic); this form
+// makes no bit-exactness claim.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(W * 32)
+eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                        const double* __restrict__ A, double* __restrict__ out, int64_t ldo,
+                        double scale, int accumulate, const int* __restrict__ perm) {
+    constexpr int KIND = SGM_HIER_PW_LINEAR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+    }
+    double* bas_all = sknots + 2 * (size_t)pl.n_knots;
+    double* sPart = bas_all + (size_t)pl.B * 32;              // [W][32]
+    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sPart + (size_t)W * 32);
+    const double* bas = bas_all + lane;
+    const unsigned short* idx = idx_all + lane;
+    const int4* rec4 = reinterpret_cast<const int4*>(pl.rec);
+    const int per_warp = (pl.T + W - 1) / W;
+    const int t_begin = min(pl.T, warp * per_warp), t_end = min(pl.T, t_begin + per_warp);
+
+    const int64_t n_tiles = (P + 31) >> 5;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t slot = (tile << 5) + lane;
+        const bool valid = slot < P;
+        const int64_t p = perm ? (int64_t)perm[valid ? slot : P - 1] : (valid ? slot : P - 1);
+        const double* xp = x + p * ldx;
+        __syncthreads();
+        for (int e = warp; e < pl.E; e += W) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
+                                             idx_all + lane, e, 32, pl.flags);
+        }
+        __syncthreads();
+        double acc = 0.0;
+        double w0 = 1.0, w1 = 1.0, w2 = 1.0, w3 = 1.0;         // weight prefixes
+        unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;                // offset prefixes
+        // terms are processed in batches of U: all records are fetched first, the prefix
+        // updates run in order, the U table gathers are in flight together, then the FMAs
+        constexpr int U = 4;
+        for (int tb = t_begin; tb < t_end; tb += U) {
+            int4 r0[U], r1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = min(tb + u, t_end - 1);
+                r0[u] = __ldg(rec4 + 2 * t);
+                r1[u] = __ldg(rec4 + 2 * t + 1);
+            }
+            double wv[U];
+            const double* av[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = r0[u].w & 0xff;
+                const int cp = (tb + u == t_begin) ? 0 : ((r0[u].w >> 12) & 7);
+                if (tb + u < t_end) {
+                    if (k > 0 && cp < 1) {
+                        const unsigned e = (unsigned)r1[u].x & 0xffffu;
+                        w0 = bas[e * 32];
+                        o0 = (unsigned)idx[e * 32] * ((unsigned)r1[u].z & 0xffffu);
+                    }
+                    if (k > 1 && cp < 2) {
+                        const unsigned e = (unsigned)r1[u].x >> 16;
+                        w1 = w0 * bas[e * 32];
+                        o1 = o0 + (unsigned)idx[e * 32] * ((unsigned)r1[u].z >> 16);
+                    }
+                    if (k > 2 && cp < 3) {
+                        const unsigned e = (unsigned)r1[u].y & 0xffffu;
+                        w2 = w1 * bas[e * 32];
+                        o2 = o1 + (unsigned)idx[e * 32] * ((unsigned)r1[u].w & 0xffffu);
+                    }
+                    if (k > 3) {
+                        const unsigned e = (unsigned)r1[u].y >> 16;
+                        w3 = w2 * bas[e * 32];
+                        o3 = o2 + (unsigned)idx[e * 32] * ((unsigned)r1[u].w >> 16);
+                    }
+                }
+                wv[u] = k == 0 ? 1.0 : (k == 1 ? w0 : (k == 2 ? w1 : (k == 3 ? w2 : w3)));
+                const unsigned off = k == 0 ? 0u : (k == 1 ? o0 : (k == 2 ? o1 : (k == 3 ? o2 : o3)));
+                av[u] = A + r0[u].z + off;
+            }
+            double vv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) vv[u] = __ldg(av[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (tb + u < t_end) acc = fma(vv[u], wv[u], acc);
+        }
+        sPart[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (warp == 0 && valid) {
+            double o = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) o = o + sPart[ww * 32 + lane];
+            double* dst = out + p * ldo;
+            *dst = accumulate ? *dst + scale * o : scale * o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Locality sort of the evaluation points (counting sort on a <= 16-bit key).  Each point is
 // evaluated independently, so the order only changes which points share a warp: with equal
 // coarse brackets the 32 lanes of a gather hit 1-2 cache lines instead of 4-5.

@@ -138,6 +138,16 @@ class HierarchicalPlan:
         self._fam_newrank = np.concatenate(newrank[1:]) if n_fam else np.zeros(0, np.int32)
         self._term_fam = term_fam
         self._map_off = map_off
+        # the evaluation kernels address a term's surplus block with the FIRST active
+        # direction fastest (offset prefixes are then shared by consecutive multi-indices);
+        # the grid builder numbers nodes with the last direction fastest: permutation
+        maps_f = np.arange(self.M, dtype=np.int32)
+        for t in range(card):
+            lo, hi = map_off[t], map_off[t + 1]
+            shape = [newpos[ranks[t, d]].size for d in np.flatnonzero(ranks[t] > 0)]
+            if len(shape) > 1:
+                maps_f[lo:hi] = lo + np.arange(hi - lo, dtype=np.int32).reshape(shape).ravel(order="F")
+        self._maps_f = maps_f
         self._device = {}
 
     def _find_parents(self, nodes, ch, d, coord):
@@ -155,7 +165,7 @@ class HierarchicalPlan:
         if device not in self._device:
             dev = torch.device("cuda", device)
             plan = DevicePlan(_lib.KIND_HIER_LINEAR, self.it.N, self.M, np.ones(self._term_fam.shape[0]),
-                              self._term_fam, self._map_off, np.arange(self.M, dtype=np.int32),
+                              self._term_fam, self._map_off, self._maps_f,
                               self._fam_off, self._fam_knots, device=device,
                               fam_newrank=self._fam_newrank)
             batches = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in self.batches]

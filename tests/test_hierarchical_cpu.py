@@ -33,8 +33,8 @@ def emulate(hp, x, f):
             lo_new = nr[i] >= 0
             w = w * np.where(lo_new, 1 - y, y)
             j = np.where(lo_new, nr[i], nr[i + 1])
-            off = off + j * int(np.prod(sizes[a + 1:], dtype=np.int64))
-        out += alpha[hp._map_off[t] + off] * w[:, None]
+            off = off + j * int(np.prod(sizes[:a], dtype=np.int64))      # first direction fastest
+        out += alpha[hp._maps_f[hp._map_off[t] + off]] * w[:, None]
     return out
 
 
