@@ -519,6 +519,28 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         while (cp < kk && cp < 3 && r.ent[cp] == q.ent[cp]) ++cp;
         r.info |= cp << 12;
     }
+    // hierarchical form: a second copy of the records grouped by the number of directions
+    // (stable, so every group stays lexicographic), with the common prefixes recomputed
+    std::vector<TermRec> hrec;
+    int hgroup[6] = {0, 0, 0, 0, 0, 0};
+    if (kind == SGM_HIER_PW_LINEAR && n_packed == T) {
+        for (int kk = 0; kk <= 4; ++kk) {
+            hgroup[kk] = (int)hrec.size();
+            for (int64_t t = 0; t < T; ++t)
+                if ((rec[t].info & 0xff) == kk) {
+                    TermRec r = rec[t];
+                    r.info &= ~(7 << 12);
+                    if ((int)hrec.size() > hgroup[kk]) {
+                        const TermRec& q = hrec.back();
+                        int cp = 0;
+                        while (cp < kk && cp < 3 && r.ent[cp] == q.ent[cp]) ++cp;
+                        r.info |= cp << 12;
+                    }
+                    hrec.push_back(r);
+                }
+        }
+        hgroup[5] = (int)hrec.size();
+    }
     for (int64_t i = 0; i < desc->map_off[T]; ++i)
         if (desc->maps[i] < 0 || desc->maps[i] >= desc->M)
             return sgm_fail(SGM_ERR_INVALID, "plan_create: map entry outside [0, M)");
@@ -587,7 +609,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     int rc = SGM_OK;
     const unsigned* cflags = nullptr;
     if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
-        (rc = upload(plan, rec, &d.rec)) ||
+        (rc = upload(plan, rec, &d.rec)) || (rc = upload(plan, hrec, &d.hrec)) ||
         (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
         (rc = upload(plan, maps, &d.maps)) ||
         (rc = upload(plan, corner_term, &d.corner_term)) ||
@@ -597,6 +619,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         return rc;
     }
     d.flags = const_cast<unsigned*>(cflags);
+    for (int i = 0; i < 6; ++i) d.hgroup[i] = hgroup[i];
     *out = plan;
     return SGM_OK;
 }

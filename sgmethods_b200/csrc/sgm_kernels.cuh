@@ -66,6 +66,8 @@ struct PlanDev {
     const double* knots;
     const double* lambda;
     const short* newrank;              // SGM_HIER_PW_LINEAR: rank of a knot among the new knots, -1 old
+    const TermRec* hrec;               // SGM_HIER_PW_LINEAR: records grouped by number of directions
+    int hgroup[6];                     // hrec[hgroup[k] .. hgroup[k+1]) = terms with k directions
     unsigned* flags;
     // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
     // coarsest knot family used in that direction), for the n_key most used directions
@@ -513,6 +515,54 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
 // reusable.  Partial sums of the W warps are added in warp order (deterministic); this form
 // makes no bit-exactness claim.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int hrec4_val(const TermRec* hrec, int t) {
+    return __ldg(reinterpret_cast<const int4*>(hrec) + 2 * t).z;
+}
+// all multi-indices with exactly K active directions, split in contiguous ranges over W warps
+template <int K, int W>
+__device__ __forceinline__ double hier_group(const PlanDev& pl, int warp, const double* bas,
+                                             const unsigned short* idx,
+                                             const double* __restrict__ A) {
+    const int g0 = pl.hgroup[K], g1 = pl.hgroup[K + 1];
+    const int per_warp = (g1 - g0 + W - 1) / W;
+    const int t_begin = min(g1, g0 + warp * per_warp), t_end = min(g1, t_begin + per_warp);
+    const int4* rec4 = reinterpret_cast<const int4*>(pl.hrec);
+    double acc = 0.0;
+    double w0 = 1.0, w1 = 1.0, w2 = 1.0;
+    unsigned o0 = 0, o1 = 0, o2 = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int4 r0 = __ldg(rec4 + 2 * t);
+        const int4 r1 = __ldg(rec4 + 2 * t + 1);
+        const int cp = (t == t_begin) ? 0 : ((r0.w >> 12) & 7);
+        if (K >= 2 && cp < 1) {
+            const unsigned e = (unsigned)r1.x & 0xffffu;
+            w0 = bas[e * 32];
+            o0 = (unsigned)idx[e * 32] * ((unsigned)r1.z & 0xffffu);
+        }
+        if (K >= 3 && cp < 2) {
+            const unsigned e = (unsigned)r1.x >> 16;
+            w1 = w0 * bas[e * 32];
+            o1 = o0 + (unsigned)idx[e * 32] * ((unsigned)r1.z >> 16);
+        }
+        if (K >= 4 && cp < 3) {
+            const unsigned e = (unsigned)r1.y & 0xffffu;
+            w2 = w1 * bas[e * 32];
+            o2 = o1 + (unsigned)idx[e * 32] * ((unsigned)r1.w & 0xffffu);
+        }
+        // last direction: always evaluated
+        const unsigned el = K == 1 ? ((unsigned)r1.x & 0xffffu) : K == 2 ? ((unsigned)r1.x >> 16)
+                          : K == 3 ? ((unsigned)r1.y & 0xffffu) : ((unsigned)r1.y >> 16);
+        const unsigned sl = K == 1 ? ((unsigned)r1.z & 0xffffu) : K == 2 ? ((unsigned)r1.z >> 16)
+                          : K == 3 ? ((unsigned)r1.w & 0xffffu) : ((unsigned)r1.w >> 16);
+        const double wp = K == 1 ? 1.0 : K == 2 ? w0 : K == 3 ? w1 : w2;
+        const unsigned op = K == 1 ? 0u : K == 2 ? o0 : K == 3 ? o1 : o2;
+        const double w = K == 1 ? bas[el * 32] : wp * bas[el * 32];
+        const unsigned off = op + (unsigned)idx[el * 32] * sl;
+        acc = fma(__ldg(A + r0.z + off), w, acc);
+    }
+    return acc;
+}
+
 template <int W>
 __global__ void __launch_bounds__(W * 32)
 eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
@@ -533,9 +583,6 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
     unsigned short* idx_all = reinterpret_cast<unsigned short*>(sPart + (size_t)W * 32);
     const double* bas = bas_all + lane;
     const unsigned short* idx = idx_all + lane;
-    const int4* rec4 = reinterpret_cast<const int4*>(pl.rec);
-    const int per_warp = (pl.T + W - 1) / W;
-    const int t_begin = min(pl.T, warp * per_warp), t_end = min(pl.T, t_begin + per_warp);
 
     const int64_t n_tiles = (P + 31) >> 5;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -550,59 +597,14 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
                                              idx_all + lane, e, 32, pl.flags);
         }
         __syncthreads();
-        double acc = 0.0;
-        double w0 = 1.0, w1 = 1.0, w2 = 1.0, w3 = 1.0;         // weight prefixes
-        unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;                // offset prefixes
-        // terms are processed in batches of U: all records are fetched first, the prefix
-        // updates run in order, the U table gathers are in flight together, then the FMAs
-        constexpr int U = 4;
-        for (int tb = t_begin; tb < t_end; tb += U) {
-            int4 r0[U], r1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = min(tb + u, t_end - 1);
-                r0[u] = __ldg(rec4 + 2 * t);
-                r1[u] = __ldg(rec4 + 2 * t + 1);
-            }
-            double wv[U];
-            const double* av[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = r0[u].w & 0xff;
-                const int cp = (tb + u == t_begin) ? 0 : ((r0[u].w >> 12) & 7);
-                if (tb + u < t_end) {
-                    if (k > 0 && cp < 1) {
-                        const unsigned e = (unsigned)r1[u].x & 0xffffu;
-                        w0 = bas[e * 32];
-                        o0 = (unsigned)idx[e * 32] * ((unsigned)r1[u].z & 0xffffu);
-                    }
-                    if (k > 1 && cp < 2) {
-                        const unsigned e = (unsigned)r1[u].x >> 16;
-                        w1 = w0 * bas[e * 32];
-                        o1 = o0 + (unsigned)idx[e * 32] * ((unsigned)r1[u].z >> 16);
-                    }
-                    if (k > 2 && cp < 3) {
-                        const unsigned e = (unsigned)r1[u].y & 0xffffu;
-                        w2 = w1 * bas[e * 32];
-                        o2 = o1 + (unsigned)idx[e * 32] * ((unsigned)r1[u].w & 0xffffu);
-                    }
-                    if (k > 3) {
-                        const unsigned e = (unsigned)r1[u].y >> 16;
-                        w3 = w2 * bas[e * 32];
-                        o3 = o2 + (unsigned)idx[e * 32] * ((unsigned)r1[u].w >> 16);
-                    }
-                }
-                wv[u] = k == 0 ? 1.0 : (k == 1 ? w0 : (k == 2 ? w1 : (k == 3 ? w2 : w3)));
-                const unsigned off = k == 0 ? 0u : (k == 1 ? o0 : (k == 2 ? o1 : (k == 3 ? o2 : o3)));
-                av[u] = A + r0[u].z + off;
-            }
-            double vv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) vv[u] = __ldg(av[u]);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (tb + u < t_end) acc = fma(vv[u], wv[u], acc);
-        }
+        // the multi-indices are grouped by their number k of active directions (the order of
+        // the sum is free in this form); inside a group they stay lexicographic, so that
+        // consecutive ones share their leading directions.  One specialised loop per k.
+        double acc = pl.hgroup[1] > pl.hgroup[0] && warp == 0 ? __ldg(A + hrec4_val(pl.hrec, pl.hgroup[0])) : 0.0;
+        acc += hier_group<1, W>(pl, warp, bas, idx, A);
+        acc += hier_group<2, W>(pl, warp, bas, idx, A);
+        acc += hier_group<3, W>(pl, warp, bas, idx, A);
+        acc += hier_group<4, W>(pl, warp, bas, idx, A);
         sPart[warp * 32 + lane] = acc;
         __syncthreads();
         if (warp == 0 && valid) {
