@@ -546,3 +546,25 @@ def test_hierarchical_form_smooth_function_vs_long_double():
     err_fast = float(np.max(np.abs(fast - truth)))
     print(f"float64 combination formula err {err_exact:.2e}, hierarchical form err {err_fast:.2e}")
     assert err_fast <= max(err_exact, 1e-15) * 1.5
+
+
+def test_basis_tables_larger_than_shared_memory_use_the_global_scratch():
+    """Lagrange with up to 257 knots per direction: the per-point basis table (~12 KB) does
+    not fit shared memory for a 32-point tile, so the thread-per-point kernel keeps it in
+    its per-block global scratch (eval_points_kernel<.., GLOBAL_BASIS=true>)."""
+    rng = np.random.default_rng(31)
+    knots = lambda n: np.atleast_1d(np.asarray(nodes_1d.cc_nodes(n), dtype=float))  # noqa: E731
+    S = mis.smolyak_mid_set(8, 3)
+    S = S[(S.max(axis=1) == S.sum(axis=1))]          # axis-aligned indices only: 25 cheap terms
+    S = S[np.lexsort(np.rot90(S))]
+    it = SGInterpolant(S, knots, lambda n: np.where(n == 0, 1, 2 ** n + 1),
+                       tp_interpolant=TPLagrangeInterpolator, verbose=False)
+    assert it._fam_m.max() == 257
+    x = rng.uniform(-1, 1, (700, 3))
+    f = rng.normal(size=(it.num_nodes, 1))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x, f, "lagrange")
+    got = it.interpolate(x, f)
+    assert rel_err(got, ref) <= TOL
+    fv = rng.normal(size=(it.num_nodes, 4))
+    refv = sg_oracle.interpolate(oracle_plan_of(it), x[:64], fv, "lagrange")
+    assert rel_err(it.interpolate(x[:64], fv), refv) <= TOL
