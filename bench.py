@@ -340,6 +340,15 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * P * NF * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    # the drop-in call exactly as a reference user makes it: numpy in, numpy out (pageable
+    # host memory, staged through pinned buffers by the library); wall clock, rank-local
+    x_np, f_np = x_host.numpy(), f_host.numpy()
+    it.interpolate(x_np, f_np)
+    t_np = time.perf_counter()
+    for _ in range(3):
+        res_np = it.interpolate(x_np, f_np)
+    numpy_ms = (time.perf_counter() - t_np) / 3 * 1e3
+    assert np.array_equal(res_np.reshape(P, NF), out_host.numpy())
     assert torch.equal(out_host.to(dev), out), "e2e result differs from the device-resident run"
 
     gather_ms = None
@@ -380,7 +389,10 @@ def main():
             "gpu_launches": 5 * args.steps,   # pregather, sort hist/scan/scatter, eval
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
-                    "d2h_bytes_per_step": int(P * NF * 8), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(P * NF * 8), "steps": e2e_steps,
+                    "numpy_in_numpy_out": {"value": P * NF / (numpy_ms * 1e-3), "ms_per_call": numpy_ms,
+                                           "note": "SGInterpolant.interpolate(ndarray, ndarray) -> "
+                                                   "ndarray on rank 0, pageable memory, wall clock"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P)),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the "

@@ -231,25 +231,43 @@ class SGInterpolant:
         return self._device_plans[device]
 
     def _interpolate_pipelined(self, torch, plan, x_host, f, device):
-        """Pinned host points: copy them in chunks on a side stream while the previous chunk
-        is being evaluated (the kernels stay on the current stream, in order)."""
+        """Host points (pinned torch tensor, or numpy array staged through two pinned
+        buffers): the chunks are copied on a side stream while the previous chunk is being
+        evaluated; the kernels stay on the current stream, in order."""
         P, NF = x_host.shape[0], f.shape[1]
         out = torch.empty((P, NF), dtype=torch.float64, device=device)
         compute = torch.cuda.current_stream(device)
         copier = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device)
         copier.wait_stream(compute)
-        staged = []
-        for lo in range(0, P, _H2D_CHUNK):
+        is_numpy = isinstance(x_host, np.ndarray)
+        if is_numpy:
+            if getattr(self, "_staging", None) is None:
+                self._staging = [torch.empty((_H2D_CHUNK, self.N), dtype=torch.float64).pin_memory()
+                                 for _ in range(2)]
+                self._staging_free = [None, None]      # event: the buffer's last H2D copy is done
+        pending = []
+        for i, lo in enumerate(range(0, P, _H2D_CHUNK)):
             hi = min(P, lo + _H2D_CHUNK)
+            if is_numpy:
+                buf = self._staging[i % 2]
+                if self._staging_free[i % 2] is not None:
+                    self._staging_free[i % 2].synchronize()
+                src = buf[:hi - lo]
+                np.copyto(src.numpy(), x_host[lo:hi, :self.N], casting="same_kind")
+            else:
+                src = x_host[lo:hi, :self.N]
             with torch.cuda.stream(copier):
-                xd = x_host[lo:hi, :self.N].to(device, non_blocking=True)
+                xd = src.to(device, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(copier)
-            staged.append((lo, hi, xd, done))
-        for lo, hi, xd, done in staged:
+            if is_numpy:
+                self._staging_free[i % 2] = done
+            # enqueue the evaluation of this chunk right away so that it overlaps the host
+            # side staging copy of the next one
             compute.wait_event(done)
             xd.record_stream(compute)
             plan.eval(xd, f, out[lo:hi])
+            pending.append(xd)
         return out
 
     def _check_operator_constraints(self):
@@ -297,7 +315,9 @@ class SGInterpolant:
         host_rows = x_new.shape[0] if hasattr(x_new, "shape") and len(x_new.shape) == 2 else 0
         pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
             x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
-        if pinned and host_rows >= 4 * _H2D_CHUNK:
+        big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
+            x_new.dtype == np.float64 and x_new.shape[1] >= self.N
+        if (pinned or big_numpy) and host_rows >= 4 * _H2D_CHUNK:
             out = self._interpolate_pipelined(torch, plan, x_new, f, device)
         else:
             if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):

@@ -568,3 +568,18 @@ def test_basis_tables_larger_than_shared_memory_use_the_global_scratch():
     fv = rng.normal(size=(it.num_nodes, 4))
     refv = sg_oracle.interpolate(oracle_plan_of(it), x[:64], fv, "lagrange")
     assert rel_err(it.interpolate(x[:64], fv), refv) <= TOL
+
+
+def test_pipelined_numpy_path_equals_device_path():
+    """Large numpy inputs are staged through two pinned buffers; same bits as one launch."""
+    import torch
+    it = SGInterpolant(mis.smolyak_mid_set(2, 6), nodes_1d.unbounded_nodes_nested,
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    P = 5 * 131072 + 333
+    x = np.random.default_rng(2).normal(size=(P, 8))                 # 2 unused columns
+    f = np.random.default_rng(3).normal(size=(it.num_nodes, 1))
+    got = it.interpolate(x, f)
+    ref = it.interpolate(torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda()).cpu().numpy()
+    assert isinstance(got, np.ndarray) and np.array_equal(got, ref)
+    got2 = it.interpolate(x[::-1].copy(), f)                          # staging buffers reused
+    assert np.array_equal(got2, ref[::-1])
