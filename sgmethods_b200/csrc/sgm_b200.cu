@@ -352,7 +352,8 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     if (!x || !f || !out) return sgm_fail(SGM_ERR_INVALID, "eval: null buffer");
     SGM_CUDA(cudaSetDevice(plan->device));
     const int kind = plan->dev.kind;
-    if (NF == 1) {
+    // one scalar evaluation (kernel A family) of column `col` of f into column `col` of out
+    auto scalar_column = [&](int64_t col) -> int {
         const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
         if (workspace_bytes < g_bytes || !workspace)
             return sgm_fail(SGM_ERR_WORKSPACE, "eval: workspace too small");
@@ -360,27 +361,55 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
         const int64_t n = plan->n_vals;
         const int gblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plan->sm_count * 8);
-        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(plan->dev.maps, n, f, ldf, 1, G);
+        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(plan->dev.maps, n, f + col, ldf, 1, G);
         SGM_CUDA(cudaGetLastError());
         const size_t sb = workspace_bytes - g_bytes;
+        double* o = out + col;
         switch (kind) {
             case SGM_PW_LINEAR:
                 if (plan->kmax > 4)
-                    return launch_points_split<sgm::SGM_LINEAR_WIDE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-                return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            case SGM_PW_QUADRATIC: return launch_points_split<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            case SGM_PW_CUBIC: return launch_points_split<SGM_PW_CUBIC>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            case SGM_HIER_PW_LINEAR: return launch_points_split<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
-            default: return launch_points_split<SGM_LAGRANGE>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch, sb, stream);
+                    return launch_points_split<sgm::SGM_LINEAR_WIDE>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
+                return launch_points_split<SGM_PW_LINEAR>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_QUADRATIC: return launch_points_split<SGM_PW_QUADRATIC>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_PW_CUBIC: return launch_points_split<SGM_PW_CUBIC>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
+            case SGM_HIER_PW_LINEAR: return launch_points_split<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
+            default: return launch_points_split<SGM_LAGRANGE>(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
         }
+    };
+    auto column_kernels = [&](const double* fc, double* oc, int64_t ncols) -> int {
+        switch (kind) {
+            case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+            case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+            case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+            case SGM_HIER_PW_LINEAR: return launch_cols<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+            default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+        }
+    };
+    if (NF == 1) return scalar_column(0);
+    // Few output columns: the lanes-across-columns kernels leave most lanes idle, so every
+    // column goes through the scalar kernel (one launch per column, the tables stay in L2).
+    // Wide outputs: full 128/256-column tiles through the column kernels, the ragged rest
+    // column by column.
+    const char* env = std::getenv("SGM_COL_LOOP_MAX");          // dev knob
+    // measured crossover against the guarded column kernel: 44..77 columns for pw-linear
+    // plans (packed fast path), 16..25 for the nested-walk kinds (tools/exp_nf*.py)
+    const bool fast_scalar = (kind == SGM_PW_LINEAR && plan->kmax <= 4) || kind == SGM_HIER_PW_LINEAR;
+    const int64_t col_loop_max = env ? std::atoll(env) : (fast_scalar ? 48 : 16);
+    const int64_t wide_cols = NF >= 128 ? (NF >= 512 ? NF / 256 * 256 : NF / 128 * 128) : 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                         (ldf % 2 == 0) && (ldo % 2 == 0);
+    int64_t done = 0;
+    if (wide_cols && aligned && plan->dev.n_corners > 0) {
+        int rc = column_kernels(f, out, wide_cols);
+        if (rc) return rc;
+        done = wide_cols;
     }
-    switch (kind) {
-        case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
-        case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
-        case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
-        case SGM_HIER_PW_LINEAR: return launch_cols<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
-        default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, f, ldf, NF, out, ldo, scale, accumulate, stream);
+    if (NF - done > col_loop_max) return column_kernels(f + done, out + done, NF - done);
+    for (int64_t c = done; c < NF; ++c) {
+        int rc = scalar_column(c);
+        if (rc) return rc;
     }
+    return SGM_OK;
 }
 
 }  // namespace
@@ -647,7 +676,7 @@ int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags) {
 }
 
 size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
-    if (!plan || NF != 1) return 256;
+    if (!plan) return 256;
     size_t bytes = align_up((size_t)plan->n_vals * 8, 256);
     const PointLaunch L = choose_point_launch(plan);
     size_t scratch = 0;
