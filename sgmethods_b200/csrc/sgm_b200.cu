@@ -316,12 +316,14 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (ldf % 2 == 0) && (ldo % 2 == 0);
     const char* nowide = std::getenv("SGM_NO_WIDE");          // dev knob
-    if (aligned && !nowide && NF >= 128 && plan->dev.n_corners > 0) {
-        const int tile = NF >= 512 ? 256 : 128;
+    if (aligned && !nowide && NF >= 64 && plan->dev.n_corners > 0) {
+        const int tile = NF >= 512 ? 256 : (NF >= 128 ? 128 : 64);
         const int64_t n_tiles = NF / tile;
         int rc = tile == 256
             ? launch_cols_wide<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
-            : launch_cols_wide<KIND, 2>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream);
+            : tile == 128
+            ? launch_cols_wide<KIND, 2>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
+            : launch_cols_wide<KIND, 1>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream);
         if (rc) return rc;
         const int64_t done = n_tiles * tile;
         if (done == NF) return SGM_OK;
@@ -391,11 +393,12 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     // Wide outputs: full 128/256-column tiles through the column kernels, the ragged rest
     // column by column.
     const char* env = std::getenv("SGM_COL_LOOP_MAX");          // dev knob
-    // measured crossover against the guarded column kernel: 44..77 columns for pw-linear
-    // plans (packed fast path), 16..25 for the nested-walk kinds (tools/exp_nf*.py)
+    // measured (tools/exp_nf*.py): the packed pw-linear scalar kernel beats every column
+    // kernel below 128 columns; for the nested-walk kinds the crossover is 16..25 columns
     const bool fast_scalar = (kind == SGM_PW_LINEAR && plan->kmax <= 4) || kind == SGM_HIER_PW_LINEAR;
-    const int64_t col_loop_max = env ? std::atoll(env) : (fast_scalar ? 48 : 16);
-    const int64_t wide_cols = NF >= 128 ? (NF >= 512 ? NF / 256 * 256 : NF / 128 * 128) : 0;
+    const int64_t col_loop_max = env ? std::atoll(env) : (fast_scalar ? 127 : 16);
+    const int64_t wide_cols = NF >= 512 ? NF / 256 * 256
+                              : (NF >= 128 ? NF / 128 * 128 : (fast_scalar ? 0 : NF / 64 * 64));
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (ldf % 2 == 0) && (ldo % 2 == 0);
     int64_t done = 0;
