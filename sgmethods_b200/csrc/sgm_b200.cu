@@ -50,6 +50,7 @@ struct sgm_plan {
     int64_t n_vals = 0;          // sum_t S_t
     int64_t corners = 0;         // sum_t C_t
     bool all_packed = false;     // every term has a packed record (needed by the H1 kernel)
+    bool prefix_ok = false;      // tables of the prefix kernel (pw-linear, all packed) are built
     int64_t table_bytes = 0;
     int kmax = 0;
     int sm_count = 148;
@@ -165,6 +166,87 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
     return best;
 }
 
+// Locality sort of the points (scratch: perm P ints | 65536 bins | keys P u16); *perm stays
+// null when the batch is too small to benefit.
+int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsigned char* scratch,
+                  size_t scratch_bytes, cudaStream_t stream, const int** perm) {
+    *perm = nullptr;
+    const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
+    if (!(P >= kSortMinPoints && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort)) return SGM_OK;
+    const size_t need = sort_scratch_bytes(P);
+    if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
+    int* perm_w = reinterpret_cast<int*>(scratch);
+    unsigned* hist = reinterpret_cast<unsigned*>(scratch + align_up((size_t)P * 4, 256));
+    unsigned short* keys = reinterpret_cast<unsigned short*>(
+        scratch + align_up((size_t)P * 4, 256) + 65536 * 4);
+    const int nbins = 1 << plan->dev.n_key;
+    SGM_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, stream));
+    const int sblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)plan->sm_count * 8);
+    sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys);
+    sgm::sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, nbins);
+    sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, perm_w);
+    SGM_CUDA(cudaGetLastError());
+    *perm = perm_w;
+    return SGM_OK;
+}
+
+// Launch shape of the prefix kernel (pw-linear, <= 4 active directions per term).
+struct PrefixLaunch { int warps; int run; size_t smem; int blocks_per_sm; SplitKernel kern; };
+
+PrefixLaunch choose_prefix_launch(const sgm_plan* plan) {
+    const PlanDev& d = plan->dev;
+    PrefixLaunch none{0, 0, 0, 0, nullptr};
+    if (!plan->prefix_ok) return none;
+    const char* env = std::getenv("SGM_PREFIX_RUN");           // dev knob: mean terms per warp run
+    const int want = env ? std::atoi(env) : 8;
+    const int warps = 8;
+    const bool balanced = !std::getenv("SGM_PREFIX_UNBALANCED");   // dev knob
+    const int cand[2] = {want, 4};
+    for (int run : cand) {
+        SplitKernel kern = run == 8 ? (balanced ? sgm::eval_points_prefix_kernel<8, 8, 3, true>
+                                                : sgm::eval_points_prefix_kernel<8, 8, 3, false>)
+                         : run == 4 ? sgm::eval_points_prefix_kernel<8, 4, 3, false> : nullptr;
+        if (!kern) continue;
+        const int chunk = warps * run;
+        const size_t smem = (size_t)chunk * 64 + (size_t)d.n_knots * 8 + (size_t)d.B * 32 * 8 +
+                            2 * (size_t)chunk * 32 * 8 + 32 * 8 + (size_t)d.E * 32 * 2 + 64;
+        if (smem > (size_t)plan->max_smem_optin) continue;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            continue;
+        int bps = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, warps * 32, smem) != cudaSuccess || bps < 1)
+            continue;
+        return PrefixLaunch{warps, run, smem, bps, kern};
+    }
+    return none;
+}
+
+// true when the scalar evaluation of this plan / batch goes through the prefix kernel (the
+// value tables are then gathered in its first-direction-fastest layout)
+bool use_prefix_kernel(const sgm_plan* plan, int64_t P) {
+    if (!plan->prefix_ok || plan->dev.kind != SGM_PW_LINEAR) return false;
+    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split" | "prefix"
+    if (force) return std::strcmp(force, "prefix") == 0 && choose_prefix_launch(plan).warps > 0;
+    if (plan->dev.T < 32 && P >= 16384) return false;         // few terms, many points: kernel A
+    return choose_prefix_launch(plan).warps > 0;
+}
+
+int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
+                         double* out, int64_t ldo, double scale, int accumulate,
+                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    const PrefixLaunch L = choose_prefix_launch(plan);
+    if (L.warps == 0) return sgm_fail(SGM_ERR_INVALID, "prefix kernel not available for this plan");
+    const int64_t tiles = (P + 31) / 32;
+    const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
+    const int* perm = nullptr;
+    int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
+    if (rc) return rc;
+    L.kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+                                                              scale, accumulate, perm);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
 template <int KIND>
 int launch_points(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
                   double* out, int64_t ldo, double scale, int accumulate, unsigned char* scratch,
@@ -175,7 +257,7 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                         double* out, int64_t ldo, double scale, int accumulate,
                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const SplitLaunch L = choose_split_launch<KIND>(plan);
-    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split"
+    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split" | "prefix"
     const bool want_v1 = force ? std::strcmp(force, "v1") == 0
                                : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
     if (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8)   // few terms / huge tables
@@ -183,24 +265,10 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
     int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
-    // locality sort of the points (scratch: perm P ints | keys P u16 | 65536 bins)
     const int* perm = nullptr;
-    const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
-    if (P >= kSortMinPoints && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort) {
-        const size_t need = sort_scratch_bytes(P);
-        if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
-        int* perm_w = reinterpret_cast<int*>(scratch);
-        unsigned* hist = reinterpret_cast<unsigned*>(scratch + align_up((size_t)P * 4, 256));
-        unsigned short* keys = reinterpret_cast<unsigned short*>(
-            scratch + align_up((size_t)P * 4, 256) + 65536 * 4);
-        const int nbins = 1 << plan->dev.n_key;
-        SGM_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, stream));
-        const int sblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)plan->sm_count * 8);
-        sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys);
-        sgm::sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, nbins);
-        sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, perm_w);
-        SGM_CUDA(cudaGetLastError());
-        perm = perm_w;
+    {
+        int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
+        if (rc) return rc;
     }
     if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !std::getenv("SGM_NO_H1")) {
         constexpr int HW = 16;
@@ -363,10 +431,14 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
         const int64_t n = plan->n_vals;
         const int gblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plan->sm_count * 8);
-        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(plan->dev.maps, n, f + col, ldf, 1, G);
+        const bool prefix = use_prefix_kernel(plan, P);
+        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(
+            prefix ? plan->dev.gmaps : plan->dev.maps, n, f + col, ldf, 1, G);
         SGM_CUDA(cudaGetLastError());
         const size_t sb = workspace_bytes - g_bytes;
         double* o = out + col;
+        if (prefix)
+            return launch_points_prefix(plan, x, P, ldx, G, o, ldo, scale, accumulate, scratch, sb, stream);
         switch (kind) {
             case SGM_PW_LINEAR:
                 if (plan->kmax > 4)
@@ -576,6 +648,93 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     for (int64_t i = 0; i < desc->map_off[T]; ++i)
         if (desc->maps[i] < 0 || desc->maps[i] >= desc->M)
             return sgm_fail(SGM_ERR_INVALID, "plan_create: map entry outside [0, M)");
+    // prefix kernel (pw-linear, every term packed): records and node map for value tables laid
+    // out with the FIRST active direction fastest, plus the number of leading entries each
+    // term shares with its predecessor
+    std::vector<TermRec> prec;
+    std::vector<int> gmaps;
+    if (kind == SGM_PW_LINEAR && n_packed == T && T > 0) {
+        prec.resize((size_t)T);
+        gmaps.resize((size_t)desc->map_off[T]);
+        bool ok = true;
+        for (int64_t t = 0; t < T && ok; ++t) {
+            const TermHdr& h = hdr[t];
+            TermRec r = rec[t];
+            if (!(r.info & sgm::TERMREC_PACKED)) { ok = false; break; }
+            int ext[4] = {1, 1, 1, 1}, cs[4] = {0, 0, 0, 0}, fs[4] = {0, 0, 0, 0};
+            int stride = 1;
+            for (int j = 0; j < h.k; ++j) {
+                const TermDim& d = tdim[h.dim_off + j];
+                ext[j] = entries[d.ent].n;
+                cs[j] = d.stride;
+                fs[j] = stride;
+                if (stride > 0xffff || d.ent > 1023) ok = false;
+                r.ent[j] = (unsigned short)(d.ent * 64);   // byte offset into the [E][32] u16 table
+                r.stride[j] = (unsigned short)stride;
+                stride *= ext[j];
+            }
+            int cp = 0;
+            if (t > 0) {
+                const int kq = prec[t - 1].info & 0xf;
+                while (cp < kq && cp < h.k - 1 && cp < 3 && r.ent[cp] == prec[t - 1].ent[cp]) ++cp;
+            }
+            r.info = h.k | (cp << 4);
+            prec[t] = r;
+            const int* src = desc->maps + h.val_off;
+            int* dst = gmaps.data() + h.val_off;
+            for (int i0 = 0; i0 < ext[0]; ++i0)
+                for (int i1 = 0; i1 < ext[1]; ++i1)
+                    for (int i2 = 0; i2 < ext[2]; ++i2)
+                        for (int i3 = 0; i3 < ext[3]; ++i3)
+                            dst[i0 * fs[0] + i1 * fs[1] + i2 * fs[2] + i3 * fs[3]] =
+                                src[i0 * cs[0] + i1 * cs[1] + i2 * cs[2] + i3 * cs[3]];
+        }
+        if (!ok) { prec.clear(); gmaps.clear(); }
+    }
+    // cost-balanced split of every 64-term chunk into 8 runs of consecutive terms (one per
+    // warp of the prefix kernel).  Cost model in issued instructions (from the SASS, then
+    // scanned on a B200 with tools/exp_cost.py -- the optimum is flat): a term costs ~45 + 4.5
+    // per corner, +35 for the first term of a run (no prefix to reuse); the warp that adds up
+    // the previous chunk's products (chunk index - 1 mod 8) carries ~2.5 per term of that
+    // chunk on top.
+    std::vector<unsigned char> run_start;
+    if (!prec.empty()) {
+        constexpr int PW = 8, PCHUNK = 64;
+        auto knob = [](const char* name, double dflt) {             // dev knobs for the cost model
+            const char* v = std::getenv(name);
+            return v ? std::atof(v) : dflt;
+        };
+        const double c_term = knob("SGM_COST_TERM", 45.0), c_corner = knob("SGM_COST_CORNER", 4.5),
+                     c_first = knob("SGM_COST_FIRST", 35.0), c_sum = knob("SGM_COST_SUM", 2.5);
+        const int64_t n_chunks = (T + PCHUNK - 1) / PCHUNK;
+        run_start.resize((size_t)n_chunks * (PW + 1));
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            const int64_t t0 = c * PCHUNK;
+            const int nt = (int)std::min<int64_t>(PCHUNK, T - t0);
+            const int prev_nt = c == 0 ? (int)(T - (n_chunks - 1) * PCHUNK) : PCHUNK;
+            const int summer = (int)((c + n_chunks - 1) % n_chunks) & (PW - 1);
+            double cost[PCHUNK], total = c_first * PW + c_sum * prev_nt;
+            for (int i = 0; i < nt; ++i) {
+                cost[i] = c_term + c_corner * hdr[t0 + i].ncorner;
+                total += cost[i];
+            }
+            unsigned char* rs = run_start.data() + c * (PW + 1);
+            int pos = 0;
+            double remaining = total;
+            for (int w = 0; w < PW; ++w) {
+                rs[w] = (unsigned char)pos;
+                const double target = remaining / (PW - w);
+                double load = c_first + (w == summer ? c_sum * prev_nt : 0.0);
+                // take terms while that brings the load closer to the target
+                while (pos < nt && (w == PW - 1 || std::fabs(load + cost[pos] - target) <= std::fabs(load - target))) {
+                    load += cost[pos];
+                    ++pos;
+                }
+                remaining -= load;
+            }
+            rs[PW] = (unsigned char)nt;
+        }
+    }
 
     int dev_count = 0;
     SGM_CUDA(cudaGetDeviceCount(&dev_count));
@@ -643,7 +802,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
         (rc = upload(plan, rec, &d.rec)) || (rc = upload(plan, hrec, &d.hrec)) ||
         (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
-        (rc = upload(plan, maps, &d.maps)) ||
+        (rc = upload(plan, maps, &d.maps)) || (rc = upload(plan, prec, &d.prec)) ||
+        (rc = upload(plan, gmaps, &d.gmaps)) || (rc = upload(plan, run_start, &d.run_start)) ||
         (rc = upload(plan, corner_term, &d.corner_term)) ||
         (rc = upload(plan, corner_off, &d.corner_off)) || (rc = upload(plan, knots, &d.knots)) ||
         (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, newrank, &d.newrank)) || (rc = upload(plan, flags, &cflags))) {
@@ -651,6 +811,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         return rc;
     }
     d.flags = const_cast<unsigned*>(cflags);
+    plan->prefix_ok = !prec.empty();
+    if (!plan->prefix_ok) { d.prec = nullptr; d.gmaps = nullptr; d.run_start = nullptr; }
     for (int i = 0; i < 6; ++i) d.hgroup[i] = hgroup[i];
     *out = plan;
     return SGM_OK;

@@ -60,7 +60,10 @@ struct PlanDev {
     const double* coeff;
     const Entry* ent;
     const int* maps;
-    const int* corner_term;            // term of every entry of the global corner list
+    const TermRec* prec;               // prefix kernel: records with first-direction-fastest strides
+    const int* gmaps;                  // prefix kernel: node map in that layout (null if not built)
+    const unsigned char* run_start;    // prefix kernel <8 warps, 64-term chunks>: [chunk][9] cost-balanced run bounds
+    const int* corner_term;           // term of every entry of the global corner list
     const int* corner_off;             // T+1 prefix sums of the terms' corner counts
     int n_corners;                     // sum_t C_t (0 if the list is not built)
     const double* knots;
@@ -493,6 +496,182 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                 double o = (t0 == 0) ? 0.0 : sOut[lane];
                 for (int tl = 0; tl < nt; ++tl) o = o + sp[tl * 32];
                 if (t0 + chunk >= pl.T) {
+                    if (valid) {
+                        double* dst = out + p * ldo;
+                        *dst = accumulate ? *dst + scale * o : scale * o;
+                    }
+                } else {
+                    sOut[lane] = o;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A3 ("prefix"): the split kernel for pw-linear plans whose terms all have <= 4
+// active directions -- same block shape (32 points x W warps), same two-role accumulation
+// (p_t = c_t * tp_t parked in shared memory, out = out + p_t applied in term order by one
+// warp), same roundings.  What changes is who recomputes what:
+//   * every warp takes R CONSECUTIVE terms of a chunk.  In a lexicographically sorted index
+//     set consecutive terms share their leading (direction, level) pairs, so the weight
+//     prefixes  P2[c] = (1*a_0)*a_1,  P3[c] = P2*a_2  and the offset prefixes of the previous
+//     term stay in registers: a term reads the bracket tables of its NEW directions only and
+//     multiplies each corner weight once (the products are the same floating-point
+//     operations on the same operands as when recomputed, hence the same bits);
+//   * the value tables G are laid out with the FIRST active direction fastest (gmaps), which
+//     makes the offset prefix independent of the directions that follow;
+//   * the 32-byte term records of a chunk are staged in shared memory by a coalesced copy
+//     (double buffered, prefetched one chunk ahead) and read back as broadcasts, instead of
+//     two 16-byte warp-uniform global loads per term (8 L1 wavefronts).
+// `info` of a record: k | cp << 4, cp = number of leading entries shared with the previous
+// term (0 <= cp <= min(k_prev, k - 1), at most 3).
+// ---------------------------------------------------------------------------------------
+template <int W, int R, int BPS, bool BALANCED>
+__global__ void __launch_bounds__(W * 32, BPS)
+eval_points_prefix_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
+                          double scale, int accumulate, const int* __restrict__ perm) {
+    constexpr int CHUNK = W * R;
+    static_assert((W & (W - 1)) == 0, "W must be a power of two");
+    static_assert(2 * CHUNK <= W * 32, "one thread per 16-byte half record");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int4* sRec = reinterpret_cast<int4*>(smem_raw);                    // [2][CHUNK][2]
+    double* sknots = reinterpret_cast<double*>(sRec + 4 * CHUNK);
+    double* bas_all = sknots + pl.n_knots;                             // [B][32]
+    double* sP = bas_all + (size_t)pl.B * 32;                          // [2][CHUNK][32]
+    double* sOut = sP + 2 * (size_t)CHUNK * 32;                        // [32]
+    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sOut + 32);
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) sknots[i] = pl.knots[i];
+    const unsigned char* ybase = reinterpret_cast<const unsigned char*>(bas_all + lane);
+    const unsigned char* ibase = reinterpret_cast<const unsigned char*>(idx_all + lane);
+    const int4* rec4 = reinterpret_cast<const int4*>(pl.prec);
+    const int T = pl.T;
+    const int n_chunks = (T + CHUNK - 1) / CHUNK;
+    if ((int)threadIdx.x < 2 * min(CHUNK, T)) sRec[threadIdx.x] = __ldg(rec4 + threadIdx.x);
+
+    const int64_t n_tiles = (P + 31) >> 5;
+    unsigned gc = 0;                                           // chunk counter (block-uniform)
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t slot = (tile << 5) + lane;
+        const bool valid = slot < P;
+        const int64_t p = perm ? (int64_t)perm[valid ? slot : P - 1] : (valid ? slot : P - 1);
+        const double* xp = x + p * ldx;
+        __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
+        for (int e = warp; e < pl.E; e += W) {
+            const Entry en = pl.ent[e];
+            fill_basis<SGM_PW_LINEAR, unsigned short>(en, xp[en.dim], sknots, nullptr,
+                                                      bas_all + lane, idx_all + lane, e, 32,
+                                                      pl.flags);
+        }
+        __syncthreads();
+        if (T == 0 && warp == 0 && valid) {
+            double* o = out + p * ldo;
+            *o = accumulate ? *o + scale * 0.0 : scale * 0.0;
+        }
+        for (int c = 0; c < n_chunks; ++c, ++gc) {
+            const int t0 = c * CHUNK;
+            const int nt = min(CHUNK, T - t0);
+            {   // records of the next chunk (cyclic: the last chunk prefetches chunk 0)
+                const int tn0 = (c + 1 == n_chunks) ? 0 : t0 + CHUNK;
+                const int ntn = min(CHUNK, T - tn0);
+                if ((int)threadIdx.x < 2 * ntn)
+                    sRec[((gc + 1) & 1u) * 2 * CHUNK + threadIdx.x] = __ldg(rec4 + 2 * tn0 + threadIdx.x);
+            }
+            const int4* myrec = sRec + (gc & 1u) * 2 * CHUNK;
+            double* sp = sP + (size_t)(gc & 1u) * CHUNK * 32 + lane;
+            double P2[4], P3[8];
+            unsigned B2 = 0, B3 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) P2[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) P3[i] = 0.0;
+            // this warp's run of consecutive terms: cost-balanced bounds from the plan (the
+            // warp that is still adding up the previous chunk gets fewer terms), else R each
+            int tl_begin = warp * R, tl_end = min(nt, (warp + 1) * R);
+            if (BALANCED) {
+                tl_begin = pl.run_start[c * (W + 1) + warp];
+                tl_end = pl.run_start[c * (W + 1) + warp + 1];
+            }
+#pragma unroll 1
+            for (int tl = tl_begin; tl < tl_end; ++tl) {
+                const int4 r0 = myrec[2 * tl];                  // coeff (x,y), val_off, info
+                const int4 r1 = myrec[2 * tl + 1];              // 4 x (entry * 64) u16, 4 x stride u16
+                const int k = r0.w & 0xf;
+                const int cp = (tl == tl_begin) ? 0 : ((r0.w >> 4) & 0xf);
+                // entry fields are pre-scaled byte offsets into the u16 index table ([e][32]);
+                // the same value * 4 addresses the fp64 bracket-coordinate table
+                const unsigned f0 = (unsigned)r1.x & 0xffffu, f1 = (unsigned)r1.x >> 16,
+                               f2 = (unsigned)r1.y & 0xffffu, f3 = (unsigned)r1.y >> 16;
+                const unsigned s1 = (unsigned)r1.z >> 16, s2 = (unsigned)r1.w & 0xffffu,
+                               s3 = (unsigned)r1.w >> 16;
+#define SGM_Y(fe) (*reinterpret_cast<const double*>(ybase + 4u * (fe)))
+#define SGM_I(fe) ((unsigned)*reinterpret_cast<const unsigned short*>(ibase + (fe)))
+                double tp = 0.0;
+                if (k == 0) {
+                    tp = G[(unsigned)r0.z];
+                } else if (k == 1) {
+                    const double y = SGM_Y(f0);
+                    const double* q = G + ((unsigned)r0.z + SGM_I(f0));
+                    tp = tp + q[0] * (1.0 - y);
+                    tp = tp + q[1] * y;
+                } else {
+                    if (cp < 2) {
+                        const double y0 = SGM_Y(f0), y1 = SGM_Y(f1);
+                        const double l0 = 1.0 - y0, l1 = 1.0 - y1;
+                        P2[0] = l0 * l1; P2[1] = l0 * y1; P2[2] = y0 * l1; P2[3] = y0 * y1;
+                        B2 = SGM_I(f0) + SGM_I(f1) * s1;
+                    }
+                    if (k == 2) {
+                        const double* q = G + ((unsigned)r0.z + B2);
+                        const double* q1 = q + s1;
+                        tp = tp + q[0] * P2[0];
+                        tp = tp + q1[0] * P2[1];
+                        tp = tp + q[1] * P2[2];
+                        tp = tp + q1[1] * P2[3];
+                    } else {
+                        if (cp < 3) {
+                            const double y2 = SGM_Y(f2);
+                            const double l2 = 1.0 - y2;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                P3[2 * i] = P2[i] * l2;
+                                P3[2 * i + 1] = P2[i] * y2;
+                            }
+                            B3 = B2 + SGM_I(f2) * s2;
+                        }
+                        if (k == 3) {
+                            // corner (b0 b1 b2): address q + b0 + b1 s1 + b2 s2
+                            const double* q = G + ((unsigned)r0.z + B3);
+                            const double* a[4] = {q, q + s2, q + s1, q + (s1 + s2)};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) tp = tp + a[i & 3][i >> 2] * P3[i];
+                        } else {
+                            const double y3 = SGM_Y(f3);
+                            const double l3 = 1.0 - y3;
+                            const double* q = G + ((unsigned)r0.z + B3 + SGM_I(f3) * s3);
+                            const unsigned c12 = s1 + s2;
+                            const double* a[8] = {q, q + s3, q + s2, q + (s2 + s3),
+                                                  q + s1, q + (s1 + s3), q + c12, q + (c12 + s3)};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                tp = tp + a[2 * (i & 3)][i >> 2] * (P3[i] * l3);
+                                tp = tp + a[2 * (i & 3) + 1][i >> 2] * (P3[i] * y3);
+                            }
+                        }
+                    }
+                }
+#undef SGM_Y
+#undef SGM_I
+                sp[tl * 32] = __hiloint2double(r0.y, r0.x) * tp;
+            }
+            __syncthreads();
+            if (warp == (c & (W - 1))) {
+                double o = (c == 0) ? 0.0 : sOut[lane];
+                for (int tl = 0; tl < nt; ++tl) o = o + sp[tl * 32];
+                if (c + 1 == n_chunks) {
                     if (valid) {
                         double* dst = out + p * ldo;
                         *dst = accumulate ? *dst + scale * o : scale * o;

@@ -485,6 +485,43 @@ def test_every_scalar_kernel_flavour_against_oracle():
     assert np.array_equal(got[:400], sg_oracle.interpolate(oracle_plan_of(it), x[:400], f))
 
 
+@pytest.mark.parametrize("run", ["4", "8", "8u"])
+def test_prefix_kernel_equals_split_kernel_and_oracle(run, monkeypatch):
+    """The prefix kernel (consecutive terms per warp, weight / offset prefixes reused, value
+    tables first-direction-fastest) performs the same roundings as the split kernel: results
+    must be bit-identical to it and to the oracle, for every run partition (uniform runs of 4
+    or 8 terms, cost-balanced runs), with and without the locality sort, on isotropic, anisotropic and tiny index sets (ragged last chunk,
+    constant term, k = 1..4)."""
+    rng = np.random.default_rng(21)
+    l2k = lambda n: 2 ** (n + 1) - 1
+    sets = [mis.smolyak_mid_set(4, 6), mis.smolyak_mid_set(3, 9), mis.smolyak_mid_set(1, 2),
+            mis.aniso_smolyak_mid_set(5.0, 4, np.array([1.0, 1.5, 2.0, 1.2])),
+            mis.tensor_product_mid_set(2, 4)]
+    for mid in sets:
+        it = SGInterpolant(mid, nodes_1d.unbounded_nodes_nested, l2k, verbose=False)
+        f = rng.normal(size=(it.num_nodes, 1))
+        for P in (777, 33000):
+            x = rng.normal(size=(P, it.N))
+            monkeypatch.setenv("SGM_PREFIX_RUN", run.rstrip("u"))
+            if run.endswith("u"):
+                monkeypatch.setenv("SGM_PREFIX_UNBALANCED", "1")
+            monkeypatch.setenv("SGM_FORCE_KERNEL", "prefix")
+            got = it.interpolate(x, f)
+            monkeypatch.setenv("SGM_FORCE_KERNEL", "split")
+            old = it.interpolate(x, f)
+            monkeypatch.delenv("SGM_FORCE_KERNEL")
+            default = it.interpolate(x, f)
+            assert np.array_equal(got, old, equal_nan=True)
+            assert np.array_equal(default, old, equal_nan=True)
+            ref = sg_oracle.interpolate(oracle_plan_of(it), x[:500], f)
+            assert np.array_equal(got[:500], ref)
+    # two output columns go through the per-column scalar path (strided f / out)
+    it = SGInterpolant(mis.smolyak_mid_set(3, 5), nodes_1d.unbounded_nodes_nested, l2k, verbose=False)
+    f = rng.normal(size=(it.num_nodes, 3))
+    x = rng.normal(size=(1000, 5))
+    assert np.array_equal(it.interpolate(x, f), sg_oracle.interpolate(oracle_plan_of(it), x, f))
+
+
 def test_levy_ciesielski_many_levels_uses_generic_kernel():
     rng = np.random.default_rng(13)
     tt = np.linspace(0, 1, 29)
