@@ -36,8 +36,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of the evaluation kernel from the committed ncu capture
-# (136.91 MB read + 4.15 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
-NCU_TRAFFIC = {("c2", 10 ** 6): 141056000}
+# (136.03 MB read + 4.23 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
+NCU_TRAFFIC = {("c2", 10 ** 6): 140259584}
 
 METRIC = "interpolant point-evals x outputs per second (fp64)"
 UNIT = "point-evals*outputs/s"
@@ -85,11 +85,11 @@ def secondary_rooflines(P, corners, terms, kernel_ms, clk):
     """Lower bounds of the exact pw-linear scalar kernel on the on-chip resources that
     actually bind it (148 SMs): L1 data pipe 128 B/clk/SM moves one 8-byte value per corner
     (2 wavefronts per warp-wide 64-bit gather at best), FP64 pipe 64 lanes/clk/SM executes
-    ~4 operations per corner (weight product, value product, add, amortised prefix)."""
+    ~3 operations per corner with prefix reuse (one weight product, value product, add)."""
     mhz = (clk.get("sm_mhz") or 1965.0) * 1e6
     sms = 148
     t_l1 = P * corners * 8 / (128 * sms * mhz)
-    t_fp64 = P * corners * 4 / (64 * sms * mhz)
+    t_fp64 = P * corners * 3 / (64 * sms * mhz)
     t = kernel_ms * 1e-3
     return {"l1_data_pipe_floor_ms": t_l1 * 1e3, "fp64_floor_ms": t_fp64 * 1e3,
             "frac_of_l1_floor": t_l1 / t, "frac_of_fp64_floor": t_fp64 / t}
@@ -397,17 +397,18 @@ def main():
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P)),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the "
                          "kernel, ncu --set full capture of this command "
-                         "(profiles/r1_v3_split_sorted_ncu_full.txt)",
+                         "(profiles/r1_v4_prefix_ncu_full.txt)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
-                         "kernel": "sgm::eval_points_split_kernel<pw-linear,16,64> (+ pregather and "
-                                   "the point locality sort, ~1% of the step)",
+                         "kernel": "sgm::eval_points_prefix_kernel<8 warps, 64-term chunks, balanced "
+                                   "runs> (+ pregather and the point locality sort, <1% of the "
+                                   "step; profiles/r1_v4_launches.csv)",
                          "kernel_ms": kernel_ms,
                          "note": "the exact combination form is bound by the SM's L1 data pipe "
                                  "(128 B/clk/SM; 8-byte corner gathers + bracket tables) and "
                                  "FP64 issue, not HBM (DESIGN.md section 5); ncu of this kernel: "
-                                 "L1 data pipe 78 %, issue 54 %, FP64 pipe 35 % of peak "
-                                 "(profiles/r1_v3_split_sorted_ncu_full.txt)",
+                                 "L1 data pipe 71 %, issue 57 %, FP64 pipe 35 % of peak "
+                                 "(profiles/r1_v4_prefix_ncu_full.txt)",
                          "corner_gathers_per_s": P * corners / (kernel_ms * 1e-3),
                          "secondary": secondary_rooflines(P, corners, len(it._coeffs),
                                                           kernel_ms, clocks.summary())},

@@ -51,6 +51,7 @@ struct sgm_plan {
     int64_t corners = 0;         // sum_t C_t
     bool all_packed = false;     // every term has a packed record (needed by the H1 kernel)
     bool prefix_ok = false;      // tables of the prefix kernel (pw-linear, all packed) are built
+    int prefix_wins = -1;        // cached occupancy comparison prefix vs split kernel (-1: not yet)
     int64_t table_bytes = 0;
     int kmax = 0;
     int sm_count = 148;
@@ -124,7 +125,7 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int64_t kSortMinPoints = 32768;
 size_t sort_scratch_bytes(int64_t P) {
-    return align_up((size_t)P * 4, 256) + 65536 * 4 + align_up((size_t)P * 2, 256);
+    return align_up((size_t)P * 4, 256) + 65536 * 4 + 64 * 4 + align_up((size_t)P * 2, 256);
 }
 
 // Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
@@ -166,7 +167,7 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
     return best;
 }
 
-// Locality sort of the points (scratch: perm P ints | 65536 bins | keys P u16); *perm stays
+// Locality sort of the points (scratch: perm P ints | 65536 bins | 64 block totals | keys P u16); *perm stays
 // null when the batch is too small to benefit.
 int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsigned char* scratch,
                   size_t scratch_bytes, cudaStream_t stream, const int** perm) {
@@ -177,14 +178,16 @@ int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsig
     if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
     int* perm_w = reinterpret_cast<int*>(scratch);
     unsigned* hist = reinterpret_cast<unsigned*>(scratch + align_up((size_t)P * 4, 256));
+    unsigned* block_total = hist + 65536;
     unsigned short* keys = reinterpret_cast<unsigned short*>(
-        scratch + align_up((size_t)P * 4, 256) + 65536 * 4);
+        scratch + align_up((size_t)P * 4, 256) + 65536 * 4 + 64 * 4);
     const int nbins = 1 << plan->dev.n_key;
+    const int scan_blocks = (nbins + 1023) / 1024;
     SGM_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, stream));
     const int sblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)plan->sm_count * 8);
     sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys);
-    sgm::sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, nbins);
-    sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, perm_w);
+    sgm::sort_scan_kernel<<<scan_blocks, 1024, 0, stream>>>(hist, nbins, block_total);
+    sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, block_total, scan_blocks, perm_w);
     SGM_CUDA(cudaGetLastError());
     *perm = perm_w;
     return SGM_OK;
@@ -223,12 +226,20 @@ PrefixLaunch choose_prefix_launch(const sgm_plan* plan) {
 
 // true when the scalar evaluation of this plan / batch goes through the prefix kernel (the
 // value tables are then gathered in its first-direction-fastest layout)
-bool use_prefix_kernel(const sgm_plan* plan, int64_t P) {
+bool use_prefix_kernel(sgm_plan* plan, int64_t P) {
     if (!plan->prefix_ok || plan->dev.kind != SGM_PW_LINEAR) return false;
     const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split" | "prefix"
     if (force) return std::strcmp(force, "prefix") == 0 && choose_prefix_launch(plan).warps > 0;
     if (plan->dev.T < 32 && P >= 16384) return false;         // few terms, many points: kernel A
-    return choose_prefix_launch(plan).warps > 0;
+    // large bracket tables (many directions x levels) limit the resident blocks: the split
+    // kernel's 16-warp blocks then keep more warps on the SM, which matters more than the
+    // prefix reuse (config 5, d=128: 8 vs 16 resident warps, 110 vs 85 ms per 10^5 points)
+    if (plan->prefix_wins < 0) {                              // decided once per plan
+        const PrefixLaunch L = choose_prefix_launch(plan);
+        const SplitLaunch S = choose_split_launch<SGM_PW_LINEAR>(plan);
+        plan->prefix_wins = L.warps > 0 && 4 * L.warps * L.blocks_per_sm >= 3 * S.warps * S.blocks_per_sm;
+    }
+    return plan->prefix_wins > 0;
 }
 
 int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,

@@ -816,33 +816,51 @@ __global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x,
         atomicAdd(hist + key, 1u);
     }
 }
-// exclusive scan of `n` (<= 65536) bins by one block of 1024 threads
-__global__ void sort_scan_kernel(unsigned* __restrict__ hist, int n) {
-    __shared__ unsigned part[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(n, lo + per);
-    unsigned sum = 0;
-    for (int i = lo; i < hi; ++i) sum += hist[i];
-    part[threadIdx.x] = sum;
+// exclusive scan of the bins, two levels: every block scans 1024 consecutive bins in place
+// (coalesced) and publishes its total; the scatter kernel adds the totals of the blocks
+// before a bin's block (at most 64 of them).
+__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* __restrict__ hist, int n,
+                                                         unsigned* __restrict__ block_total) {
+    __shared__ unsigned wsum[32];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v = i < n ? hist[i] : 0u;
+    unsigned inc = v;                                          // inclusive scan inside the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        unsigned v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (warp == 0) {
+        unsigned w = wsum[lane], winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += u;
+        }
+        wsum[lane] = winc - w;                                 // exclusive prefix of the warps
+        if (lane == 31) block_total[blockIdx.x] = winc;
     }
-    unsigned run = part[threadIdx.x] - sum;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
+    __syncthreads();
+    if (i < n) hist[i] = wsum[warp] + inc - v;
 }
 __global__ void sort_scatter_kernel(const unsigned short* __restrict__ keys, int64_t P,
-                                    unsigned* __restrict__ offs, int* __restrict__ perm) {
+                                    unsigned* __restrict__ offs,
+                                    const unsigned* __restrict__ block_total, int n_blocks,
+                                    int* __restrict__ perm) {
+    __shared__ unsigned base[64];
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = 0; b < n_blocks; ++b) { base[b] = run; run += block_total[b]; }
+    }
+    __syncthreads();
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
-         p += (int64_t)gridDim.x * blockDim.x)
-        perm[atomicAdd(offs + keys[p], 1u)] = (int)p;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned key = keys[p];
+        perm[base[key >> 10] + atomicAdd(offs + key, 1u)] = (int)p;
+    }
 }
 
 // G[j, 0:NF] = f[maps[j], 0:NF]  (the reference's per-term fancy-index copy,

@@ -168,6 +168,73 @@ def test_properties_at_config2_size():
     assert torch.equal(o1, it.interpolate(x, f1))
 
 
+def test_config5_shape_d128_1e5_terms_against_oracle_and_properties():
+    """BASELINE config 5 shape: d=128, 91 929 combination terms, 721 697 nodes (coefficients
+    between -79127 and 3081), scalar output.  A few points bit for bit against the oracle's
+    term loop; partition of unity and reproduction of the nodal values on a larger batch."""
+    import torch
+    S = mis.aniso_smolyak_mid_set(3, 128, np.array([1.0] * 80 + [3.0] * 48))
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1,
+                       verbose=False)
+    assert len(it.combination_coeffs) == 91929 and it.num_nodes == 721697
+    rng = np.random.default_rng(31)
+    f = rng.normal(size=(it.num_nodes, 1))
+    x = rng.normal(size=(40000, 128))
+    got = it.interpolate(x, f)
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:6], f)
+    assert np.array_equal(got[:6], ref)
+    assert np.all(np.isfinite(got))
+    ones = it.interpolate(x, np.ones_like(f))
+    assert np.max(np.abs(ones - 1.0)) <= 1e-8                       # sum_t c_t = 1
+    pick = rng.choice(it.num_nodes, 40000, replace=False)
+    at_nodes = it.interpolate(it.SG[pick], f)
+    assert np.max(np.abs(at_nodes - f[pick, 0])) <= 1e-7 * np.max(np.abs(f))
+
+
+def test_config3_shape_d64_vector_valued_against_oracle():
+    """BASELINE config 3 shape: Levy-Ciesielski anisotropy in d=64 (802 terms, 16 033 nodes),
+    NF = 10^4 output columns: a few points against the oracle on every column, partition of
+    unity on a larger batch."""
+    import torch
+    from sgmethods_b200.utils import compute_level_lc
+    a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
+    it = SGInterpolant(mis.aniso_smolyak_mid_set(10, 64, a),
+                       lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2),
+                       lambda n: 2 ** (n + 1) - 1, verbose=False)
+    assert len(it.combination_coeffs) == 802 and it.num_nodes == 16033
+    NF = 10 ** 4
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(5)
+    f = torch.randn((it.num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
+    x = torch.randn((3000, 64), dtype=torch.float64, device=dev, generator=gen)
+    got = it.interpolate(x, f)
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:12].cpu().numpy(), f.cpu().numpy())
+    assert rel_err(got[:12].cpu().numpy(), ref) <= TOL
+    print(f"config-3 shape: bit-exact {100 * np.mean(got[:12].cpu().numpy() == ref):.1f}%")
+    ones = it.interpolate(x, torch.ones((it.num_nodes, 256), dtype=torch.float64, device=dev))
+    assert float((ones - 1.0).abs().max()) <= 1e-9
+
+
+def test_config4_shape_multilevel_quadratic_nf1000_against_oracle():
+    """BASELINE config 4 shape: 4-level multilevel interpolant, piecewise quadratic, d=8,
+    NF = 10^3 (levels k = 0..3 of the Smolyak sequence on doubling Clenshaw-Curtis knots)."""
+    from oracle import drivers_oracle
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    dbl = lambda n: np.where(n == 0, 1, 2 ** n + 1)
+    seq = [SGInterpolant(mis.smolyak_mid_set(k, 8), nodes_1d.cc_nodes, dbl,
+                         tp_interpolant=TPPwQuadraticInterpolator, verbose=False) for k in range(4)]
+    rng = np.random.default_rng(41)
+    NF = 1000
+    ml = [rng.normal(size=(seq[3 - k].num_nodes, NF)) for k in range(4)]
+    yy = rng.uniform(-1, 1, (2500, 8))
+    got = MLInterpolant(seq).interpolate(yy, ml)
+    plans = [oracle_plan_of(it) for it in seq]
+    for p, it in zip(plans, seq):
+        p.SG = it.SG
+    ref = drivers_oracle.ml_interpolate(plans, "quadratic", yy[:64], ml)
+    assert rel_err(got[:64], ref) <= TOL
+
+
 def test_torch_tensors_in_torch_tensor_out_and_extra_columns():
     import torch
     g = load_golden("lin_example1")
