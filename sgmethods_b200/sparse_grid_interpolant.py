@@ -339,7 +339,10 @@ class SGInterpolant:
         return np.squeeze(out.cpu().numpy())
 
 
-_H2D_CHUNK = 131072      # rows per host->device chunk of the pipelined path
+# rows per host->device chunk of the pipelined path: a whole number of waves of the scalar
+# kernels (148 SMs x 3 blocks x 32 points x 8; also 12 waves of the 2-blocks-per-SM kernels),
+# measured best among 64k..340k rows on config 2 (tools/exp_e2e_numpy.py)
+_H2D_CHUNK = 113664
 
 
 def _to_device(torch, a, device):
