@@ -24,6 +24,13 @@ for cls, knots, lev, N, smp in cases:
             out = it.interpolate(x, rng.normal(size=(it.num_nodes, NF)))
             assert np.all(np.isfinite(out))
     print(cls.__name__, "ok")
+# prefix kernel with 4-direction terms, several chunks, ragged last chunk; and the split kernel
+it = SGInterpolant(mis.smolyak_mid_set(4, 6), nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+for P in (45, 33000):
+    a = it.interpolate(rng.normal(size=(P, 6)), rng.normal(size=(it.num_nodes, 1)))
+os.environ["SGM_FORCE_KERNEL"] = "split"
+it.interpolate(rng.normal(size=(45, 6)), rng.normal(size=(it.num_nodes, 1)))
+del os.environ["SGM_FORCE_KERNEL"]
 # few-term plan with many points -> thread-per-point kernel
 it = SGInterpolant(mis.smolyak_mid_set(1, 3), nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
 it.interpolate(rng.normal(size=(20000, 3)), rng.normal(size=(it.num_nodes, 1)))
