@@ -272,6 +272,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's version / debug lines go to stderr: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     it, desc, P_default, NF, sampler = build_workload(args.workload)
