@@ -194,11 +194,13 @@ int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsig
 }
 
 // Launch shape of the prefix kernel (pw-linear, <= 4 active directions per term).
-struct PrefixLaunch { int warps; int run; size_t smem; int blocks_per_sm; SplitKernel kern; };
+struct PrefixLaunch { int warps; int run; size_t smem; int blocks_per_sm; SplitKernel kern; int ppl; };
 
-PrefixLaunch choose_prefix_launch(const sgm_plan* plan) {
+// ppl = points per lane (1 or 2).  Two points per lane need 128 registers and twice the shared
+// memory per block: taken only if two such blocks still fit on an SM.
+PrefixLaunch choose_prefix_launch(const sgm_plan* plan, int ppl = 1) {
     const PlanDev& d = plan->dev;
-    PrefixLaunch none{0, 0, 0, 0, nullptr};
+    PrefixLaunch none{0, 0, 0, 0, nullptr, 1};
     if (!plan->prefix_ok) return none;
     const char* env = std::getenv("SGM_PREFIX_RUN");           // dev knob: mean terms per warp run
     const int want = env ? std::atoi(env) : 8;
@@ -206,20 +208,24 @@ PrefixLaunch choose_prefix_launch(const sgm_plan* plan) {
     const bool balanced = !std::getenv("SGM_PREFIX_UNBALANCED");   // dev knob
     const int cand[2] = {want, 4};
     for (int run : cand) {
-        SplitKernel kern = run == 8 ? (balanced ? sgm::eval_points_prefix_kernel<8, 8, 3, true>
-                                                : sgm::eval_points_prefix_kernel<8, 8, 3, false>)
-                         : run == 4 ? sgm::eval_points_prefix_kernel<8, 4, 3, false> : nullptr;
+        SplitKernel kern = nullptr;
+        if (run == 8 && ppl == 2) kern = sgm::eval_points_prefix_kernel<8, 8, 2, true, 2>;
+        else if (run == 8 && ppl == 1)
+            kern = balanced ? sgm::eval_points_prefix_kernel<8, 8, 3, true> : sgm::eval_points_prefix_kernel<8, 8, 3, false>;
+        else if (run == 4 && ppl == 1) kern = sgm::eval_points_prefix_kernel<8, 4, 3, false>;
         if (!kern) continue;
         const int chunk = warps * run;
-        const size_t smem = (size_t)chunk * 64 + (size_t)d.n_knots * 8 + (size_t)d.B * 32 * 8 +
-                            2 * (size_t)chunk * 32 * 8 + 32 * 8 + (size_t)d.E * 32 * 2 + 64;
+        const size_t tpts = 32 * (size_t)ppl;
+        const size_t smem = (size_t)chunk * 64 + (size_t)d.n_knots * 8 + (size_t)d.B * tpts * 8 +
+                            2 * (size_t)chunk * tpts * 8 + tpts * 8 + (size_t)d.E * tpts * 2 + 64;
         if (smem > (size_t)plan->max_smem_optin) continue;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             continue;
         int bps = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, warps * 32, smem) != cudaSuccess || bps < 1)
             continue;
-        return PrefixLaunch{warps, run, smem, bps, kern};
+        if (ppl == 2 && bps < 2) continue;
+        return PrefixLaunch{warps, run, smem, bps, kern, ppl};
     }
     return none;
 }
@@ -245,9 +251,16 @@ bool use_prefix_kernel(sgm_plan* plan, int64_t P) {
 int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
                          double* out, int64_t ldo, double scale, int accumulate,
                          unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
-    const PrefixLaunch L = choose_prefix_launch(plan);
+    PrefixLaunch L = choose_prefix_launch(plan);
     if (L.warps == 0) return sgm_fail(SGM_ERR_INVALID, "prefix kernel not available for this plan");
-    const int64_t tiles = (P + 31) / 32;
+    {   // two points per lane once the batch fills every SM with such tiles (config 2: 27.7 ->
+        // 25.0 ms); smaller batches keep 32-point tiles for the parallelism
+        const char* env_ppl = std::getenv("SGM_PREFIX_PPL");   // dev knob: force 1 | 2
+        const PrefixLaunch L2 = choose_prefix_launch(plan, 2);
+        const bool fills = P >= (int64_t)64 * plan->sm_count * std::max(L2.blocks_per_sm, 1);
+        if (L2.warps > 0 && (env_ppl ? std::atoi(env_ppl) == 2 : fills)) L = L2;
+    }
+    const int64_t tiles = (P + 32 * L.ppl - 1) / (32 * L.ppl);
     const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
     const int* perm = nullptr;
     int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
@@ -913,20 +926,23 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
     SGM_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t lc_smem = (size_t)sgm::LC_ROWS * d * 8;
-    if (L <= 12 && nt >= 32 && lc_smem <= 48 * 1024) {
+    const size_t lc_smem = 2 * (size_t)sgm::LC_ROWS * d * 8;  // double-buffered row groups
+    if (L <= 12 && nt >= 32 && lc_smem <= 96 * 1024) {
         const int tpt = 2;
         const int64_t gx = (nt + 256 * tpt - 1) / (256 * tpt);
-        // enough blocks to fill the GPU several times over, at least 8 rows per block
-        int64_t rows = std::max<int64_t>(sgm::LC_ROWS, (P * gx + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16));
+        // 8 blocks per SM in the grid (3 resident: 80 registers), at least 32 rows per block:
+        // measured best of 4 / 8 / 16 / 32 (tools/exp_lc2.py)
+        const int64_t per_sm = 8;
+        int64_t rows = std::max<int64_t>(sgm::LC_ROWS, (P * gx + (int64_t)sms * per_sm - 1) / ((int64_t)sms * per_sm));
         int64_t gy = (P + rows - 1) / rows;
         if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
-        if (L <= 6)
-            sgm::lc_brownian_tiles_kernel<6, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
-                tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
-        else
-            sgm::lc_brownian_tiles_kernel<12, 2><<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(
-                tt, nt, yy, P, d, ldy, T, sqrtT, level_scale, L, W, ldw, (int)rows);
+        using LcKernel = void (*)(const double*, int64_t, const double*, int64_t, int, int64_t, double,
+                                  double, const double*, int, double*, int64_t, int);
+        LcKernel kern = L > 6 ? sgm::lc_brownian_tiles_kernel<12, 2, 2> : sgm::lc_brownian_tiles_kernel<6, 2, 3>;
+        if (lc_smem > 48 * 1024)
+            SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem));
+        kern<<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(tt, nt, yy, P, d, ldy, T, sqrtT,
+                                                                     level_scale, L, W, ldw, (int)rows);
     } else {
         const int64_t total = P * nt;
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);

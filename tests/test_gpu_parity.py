@@ -552,12 +552,12 @@ def test_every_scalar_kernel_flavour_against_oracle():
     assert np.array_equal(got[:400], sg_oracle.interpolate(oracle_plan_of(it), x[:400], f))
 
 
-@pytest.mark.parametrize("run", ["4", "8", "8u"])
+@pytest.mark.parametrize("run", ["4", "8", "8u", "8p2"])
 def test_prefix_kernel_equals_split_kernel_and_oracle(run, monkeypatch):
     """The prefix kernel (consecutive terms per warp, weight / offset prefixes reused, value
     tables first-direction-fastest) performs the same roundings as the split kernel: results
     must be bit-identical to it and to the oracle, for every run partition (uniform runs of 4
-    or 8 terms, cost-balanced runs), with and without the locality sort, on isotropic, anisotropic and tiny index sets (ragged last chunk,
+    or 8 terms, cost-balanced runs, one or two points per lane), with and without the locality sort, on isotropic, anisotropic and tiny index sets (ragged last chunk,
     constant term, k = 1..4)."""
     rng = np.random.default_rng(21)
     l2k = lambda n: 2 ** (n + 1) - 1
@@ -569,7 +569,8 @@ def test_prefix_kernel_equals_split_kernel_and_oracle(run, monkeypatch):
         f = rng.normal(size=(it.num_nodes, 1))
         for P in (777, 33000):
             x = rng.normal(size=(P, it.N))
-            monkeypatch.setenv("SGM_PREFIX_RUN", run.rstrip("u"))
+            monkeypatch.setenv("SGM_PREFIX_RUN", run.rstrip("u").split("p")[0])
+            monkeypatch.setenv("SGM_PREFIX_PPL", "2" if run.endswith("p2") else "1")
             if run.endswith("u"):
                 monkeypatch.setenv("SGM_PREFIX_UNBALANCED", "1")
             monkeypatch.setenv("SGM_FORCE_KERNEL", "prefix")
