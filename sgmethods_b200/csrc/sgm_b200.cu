@@ -136,6 +136,10 @@ using SplitKernel = void (*)(const PlanDev, const double*, int64_t, int64_t, con
 
 template <int KIND>
 SplitKernel split_kernel_for(int warps, int chunk) {
+    // 1024-thread blocks (64 registers): for plans whose bracket tables leave room for one
+    // block per SM only (config 5: 128 directions, 92 KB of tables per 32 points)
+    if constexpr (KIND == SGM_PW_LINEAR)
+        if (warps == 32 && chunk == 128) return sgm::eval_points_split_kernel<KIND, 32, 128>;
     if (warps == 16 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 16, 64>;
     if (warps == 8 && chunk == 32) return sgm::eval_points_split_kernel<KIND, 8, 32>;
     if (warps == 8 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 8, 64>;
@@ -149,8 +153,9 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
                          (size_t)d.B * 32 * 8 + (size_t)d.E * 32 * 2 + 32 * 8 + 64;
     SplitLaunch best{0, 0, 0, 0};
     int best_warps = 0;
-    const int cand[4][2] = {{16, 64}, {8, 32}, {8, 64}, {4, 32}};
+    const int cand[5][2] = {{16, 64}, {8, 32}, {8, 64}, {4, 32}, {32, 128}};
     for (const auto& c : cand) {
+        if (c[0] == 32 && KIND != SGM_PW_LINEAR) continue;
         const size_t smem = fixed + 2 * (size_t)c[1] * 32 * 8;
         if (smem > (size_t)plan->max_smem_optin) continue;
         SplitKernel kern = split_kernel_for<KIND>(c[0], c[1]);
