@@ -123,7 +123,8 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr int64_t kSortMinPoints = 32768;
+constexpr int64_t kSortMinPoints = 32768;       // scalar kernels
+constexpr int64_t kSortMinPointsCols = 4096;    // wide column kernel with two points per warp
 size_t sort_scratch_bytes(int64_t P) {
     return align_up((size_t)P * 4, 256) + 65536 * 4 + 64 * 4 + align_up((size_t)P * 2, 256);
 }
@@ -175,10 +176,11 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
 // Locality sort of the points (scratch: perm P ints | 65536 bins | 64 block totals | keys P u16); *perm stays
 // null when the batch is too small to benefit.
 int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsigned char* scratch,
-                  size_t scratch_bytes, cudaStream_t stream, const int** perm) {
+                  size_t scratch_bytes, cudaStream_t stream, const int** perm,
+                  int64_t min_points = kSortMinPoints) {
     *perm = nullptr;
     const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
-    if (!(P >= kSortMinPoints && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort)) return SGM_OK;
+    if (!(P >= min_points && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort)) return SGM_OK;
     const size_t need = sort_scratch_bytes(P);
     if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
     int* perm_w = reinterpret_cast<int*>(scratch);
@@ -399,6 +401,31 @@ int launch_cols_wide(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, co
     return SGM_OK;
 }
 
+// Two points per warp (kernel C3): needs the locality permutation to pair points that read
+// the same rows of f.  Returns SGM_OK with *launched = false when the shape does not fit.
+template <int KIND, int CPL2>
+int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                      int64_t ldf, int64_t n_tiles, double* out, int64_t ldo, double scale,
+                      int accumulate, const int* perm, cudaStream_t stream, bool* launched) {
+    *launched = false;
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
+    const size_t per_warp = 2 * ((size_t)d.B * 8 + (size_t)d.E * 4);
+    const int warps = 8;
+    const size_t smem = fixed + per_warp * warps;
+    if (smem > (size_t)plan->max_smem_optin / 2) return SGM_OK;    // keep two blocks per SM
+    const int pairs_per_block = warps * 4;
+    const int64_t gx = ((P + 1) / 2 + pairs_per_block - 1) / pairs_per_block;
+    if (gx > 0x7fffffff || n_tiles > 65535) return SGM_OK;
+    auto kern = sgm::eval_cols_wide2_kernel<KIND, CPL2>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
+        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, pairs_per_block, perm);
+    SGM_CUDA(cudaGetLastError());
+    *launched = true;
+    return SGM_OK;
+}
+
 template <int KIND>
 int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                        int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
@@ -407,7 +434,7 @@ int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, 
 template <int KIND>
 int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                 int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale, int accumulate,
-                cudaStream_t stream) {
+                const int* perm, cudaStream_t stream) {
     // full 256-column (or 128-column) tiles through the wide kernel, the ragged rest through
     // the guarded kernel; needs 16-byte aligned rows
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
@@ -416,7 +443,14 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
     if (aligned && !nowide && NF >= 64 && plan->dev.n_corners > 0) {
         const int tile = NF >= 512 ? 256 : (NF >= 128 ? 128 : 64);
         const int64_t n_tiles = NF / tile;
-        int rc = tile == 256
+        const char* pairs = std::getenv("SGM_WIDE_PAIRS");     // dev knob: 0 | 1
+        bool launched = false;
+        if (tile == 256 && perm && !(pairs && pairs[0] == '0')) {
+            int rc2 = launch_cols_wide2<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale,
+                                                 accumulate, perm, stream, &launched);
+            if (rc2) return rc2;
+        }
+        int rc = launched ? SGM_OK : tile == 256
             ? launch_cols_wide<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
             : tile == 128
             ? launch_cols_wide<KIND, 2>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
@@ -480,12 +514,21 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         }
     };
     auto column_kernels = [&](const double* fc, double* oc, int64_t ncols) -> int {
+        // locality permutation of the points for the two-points-per-warp wide kernel (scratch
+        // behind the G area, shared with the scalar path: launches are ordered on the stream)
+        const int* perm = nullptr;
+        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        if (ncols >= 512 && workspace && workspace_bytes > g_bytes + sort_scratch_bytes(P)) {
+            int rc = locality_sort(plan, x, P, ldx, static_cast<unsigned char*>(workspace) + g_bytes,
+                                   workspace_bytes - g_bytes, stream, &perm, kSortMinPointsCols);
+            if (rc) return rc;
+        }
         switch (kind) {
-            case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
-            case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
-            case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
-            case SGM_HIER_PW_LINEAR: return launch_cols<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
-            default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, stream);
+            case SGM_PW_LINEAR: return launch_cols<SGM_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, perm, stream);
+            case SGM_PW_QUADRATIC: return launch_cols<SGM_PW_QUADRATIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, perm, stream);
+            case SGM_PW_CUBIC: return launch_cols<SGM_PW_CUBIC>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, perm, stream);
+            case SGM_HIER_PW_LINEAR: return launch_cols<SGM_HIER_PW_LINEAR>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, perm, stream);
+            default: return launch_cols<SGM_LAGRANGE>(plan, x, P, ldx, fc, ldf, ncols, oc, ldo, scale, accumulate, perm, stream);
         }
     };
     if (NF == 1) return scalar_column(0);
@@ -795,6 +838,15 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         for (int n = 0; n < N; ++n) if (small_fam[n] >= 0) order.push_back(n);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return usage[a] > usage[b]; });
         d.n_key = (int)std::min<size_t>(order.size(), 16);
+        // bit order (locality_key: entry 0 = most significant bit): most used direction first,
+        // so that neighbours in the sorted order differ in the least used directions; among
+        // equally used directions the LOWEST one goes last -- a differing bracket in a low
+        // direction is cheap for the prefix kernel, whose value tables are stored with the
+        // first active direction fastest (neighbouring brackets = neighbouring addresses)
+        order.resize((size_t)d.n_key);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return usage[a] != usage[b] ? usage[a] > usage[b] : a > b;
+        });
         for (int i = 0; i < d.n_key; ++i) {
             const Entry& e = entries[small_fam[order[i]]];
             d.key_dim[i] = e.dim;
@@ -880,7 +932,7 @@ size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
         scratch = (size_t)std::max<int64_t>(blocks, 1) * L.threads *
                   ((size_t)plan->dev.B * 8 + (size_t)plan->dev.E * 2);
     }
-    if (P >= kSortMinPoints) scratch = std::max(scratch, sort_scratch_bytes(P));
+    if (P >= (NF >= 64 ? kSortMinPointsCols : kSortMinPoints)) scratch = std::max(scratch, sort_scratch_bytes(P));
     return bytes + scratch + 256;
 }
 

@@ -857,7 +857,10 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned locality_key(const PlanDev& pl, const double* xp) {
     unsigned key = 0;
-    for (int i = 0; i < pl.n_key; ++i) key |= (xp[pl.key_dim[i]] >= pl.key_thr[i] ? 1u : 0u) << i;
+    // the most used direction is the most significant bit: neighbours in the sorted order then
+    // differ in the least used directions first (matters when the bins are sparsely filled)
+    for (int i = 0; i < pl.n_key; ++i)
+        key |= (xp[pl.key_dim[i]] >= pl.key_thr[i] ? 1u : 0u) << (pl.n_key - 1 - i);
     return key;
 }
 __global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
@@ -1173,6 +1176,158 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
                 r.y = old.y + r.y;
             }
             *dst = r;
+        }
+    }
+}
+
+// Kernel C3 ("wide pairs"): the wide kernel with TWO points per warp.  The points come in the
+// order of the locality permutation, so the two points of a warp mostly lie in the same
+// brackets of the coarse levels and their corner contributions read the SAME rows of f: a row
+// is then loaded once and used for both points (each with its own weight, accumulated in its
+// own registers, in the same order as when evaluated alone -- bit-identical).  This halves
+// the L1 -> register traffic that bounds the wide kernel for every shared row and doubles the
+// FP64 work in flight per load.
+template <int KIND, int CPL2>
+__global__ void __launch_bounds__(256, 2)
+eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                       const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                       int64_t ldo, double scale, int accumulate, int pairs_per_block,
+                       const int* __restrict__ perm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+    }
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
+    double* basA = sbas_all + (size_t)(2 * warp) * pl.B;
+    double* basB = basA + pl.B;
+    int* idxA = reinterpret_cast<int*>(sbas_all + (size_t)(2 * n_warps) * pl.B) + (size_t)(2 * warp) * pl.E;
+    int* idxB = idxA + pl.E;
+    __syncthreads();
+
+    // lane owns columns tile*64*CPL2 + 64*c + 2*lane + {0, 1}, c < CPL2
+    const int64_t col0 = (int64_t)blockIdx.y * (64 * CPL2) + 2 * lane;
+    const double* fcol = f + col0;
+    const int64_t n_pairs = (P + 1) >> 1;
+    const int64_t q_begin = (int64_t)blockIdx.x * pairs_per_block;
+    const int64_t q_end = min(n_pairs, q_begin + pairs_per_block);
+    for (int64_t q = q_begin + warp; q < q_end; q += n_warps) {
+        const bool hasB = 2 * q + 1 < P;
+        const int64_t pA = perm ? (int64_t)perm[2 * q] : 2 * q;
+        const int64_t pB = hasB ? (perm ? (int64_t)perm[2 * q + 1] : 2 * q + 1) : pA;
+        const double* xA = x + pA * ldx;
+        const double* xB = x + pB * ldx;
+        __syncwarp();
+        for (int e = lane; e < pl.E; e += 32) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, int>(en, xA[en.dim], sknots, slambda, basA, idxA, e, 1, pl.flags);
+            fill_basis<KIND, int>(en, xB[en.dim], sknots, slambda, basB, idxB, e, 1, pl.flags);
+        }
+        __syncwarp();
+        double2 accA[CPL2], tpA[CPL2], accB[CPL2], tpB[CPL2];
+#pragma unroll
+        for (int c = 0; c < CPL2; ++c) {
+            accA[c] = make_double2(0.0, 0.0); tpA[c] = make_double2(0.0, 0.0);
+            accB[c] = make_double2(0.0, 0.0); tpB[c] = make_double2(0.0, 0.0);
+        }
+        for (int g0 = 0; g0 < pl.n_corners; g0 += 32) {
+            const int g = g0 + lane;
+            double wA = 1.0, wB = 1.0, coef = 0.0;
+            int rowA = 0, rowB = 0, last = 0;
+            if (g < pl.n_corners) {
+                const int t = pl.corner_term[g];
+                const TermHdr h = pl.hdr[t];
+                const int cid = g - pl.corner_off[t];
+                const TermDim* td = pl.tdim + h.dim_off;
+                int offA = 0, offB = 0;
+                int cs = h.ncorner;
+                int rem = cid;
+                for (int j = 0; j < h.k; ++j) {
+                    const TermDim d = td[j];
+                    int a;
+                    if (KIND == SGM_LAGRANGE) {
+                        cs /= d.radix;
+                        a = (cid / cs) % d.radix;
+                    } else {
+                        constexpr int R = fixed_radix(KIND);
+                        cs /= R;
+                        a = rem / cs;
+                        rem -= a * cs;
+                    }
+                    wA = wA * digit_weight<KIND>(basA, 1, d, a);
+                    wB = wB * digit_weight<KIND>(basB, 1, d, a);
+                    offA += (idxA[d.ent] + a) * d.stride;
+                    offB += (idxB[d.ent] + a) * d.stride;
+                }
+                rowA = pl.maps[h.val_off + offA];
+                rowB = pl.maps[h.val_off + offB];
+                last = (cid == h.ncorner - 1);
+                if (last) coef = pl.coeff[t];
+            }
+            const int n_in = min(32, pl.n_corners - g0);
+            for (int cc = 0; cc < n_in; ++cc) {
+                const double wvA = __shfl_sync(0xffffffffu, wA, cc);
+                const double wvB = __shfl_sync(0xffffffffu, wB, cc);
+                const int rA = __shfl_sync(0xffffffffu, rowA, cc);
+                const int rB = __shfl_sync(0xffffffffu, rowB, cc);
+                const int is_last = __shfl_sync(0xffffffffu, last, cc);
+                const double* frA = fcol + (int64_t)rA * ldf;
+                double2 v[CPL2];
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c)
+                    v[c] = __ldg(reinterpret_cast<const double2*>(frA + 64 * c));
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) {
+                    tpA[c].x = tpA[c].x + v[c].x * wvA;
+                    tpA[c].y = tpA[c].y + v[c].y * wvA;
+                }
+                if (rA != rB) {                                   // warp-uniform
+                    const double* frB = fcol + (int64_t)rB * ldf;
+#pragma unroll
+                    for (int c = 0; c < CPL2; ++c)
+                        v[c] = __ldg(reinterpret_cast<const double2*>(frB + 64 * c));
+                }
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) {
+                    tpB[c].x = tpB[c].x + v[c].x * wvB;
+                    tpB[c].y = tpB[c].y + v[c].y * wvB;
+                }
+                if (is_last) {
+                    const double cf = __shfl_sync(0xffffffffu, coef, cc);
+#pragma unroll
+                    for (int c = 0; c < CPL2; ++c) {
+                        accA[c].x = accA[c].x + cf * tpA[c].x;
+                        accA[c].y = accA[c].y + cf * tpA[c].y;
+                        tpA[c] = make_double2(0.0, 0.0);
+                        accB[c].x = accB[c].x + cf * tpB[c].x;
+                        accB[c].y = accB[c].y + cf * tpB[c].y;
+                        tpB[c] = make_double2(0.0, 0.0);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int pt = 0; pt < 2; ++pt) {
+            if (pt == 1 && !hasB) break;
+            double* o = out + (pt == 0 ? pA : pB) * ldo + col0;
+#pragma unroll
+            for (int c = 0; c < CPL2; ++c) {
+                double2* dst = reinterpret_cast<double2*>(o + 64 * c);
+                const double2 a2 = pt == 0 ? accA[c] : accB[c];
+                double2 r = make_double2(scale * a2.x, scale * a2.y);
+                if (accumulate) {
+                    const double2 old = *dst;
+                    r.x = old.x + r.x;
+                    r.y = old.y + r.y;
+                }
+                *dst = r;
+            }
         }
     }
 }

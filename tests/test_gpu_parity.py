@@ -486,6 +486,31 @@ def test_vector_outputs_across_column_tile_boundaries():
     assert np.array_equal(got.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("kind", ["linear", "quadratic", "cubic", "lagrange"])
+def test_two_points_per_warp_wide_kernel_equals_one_point_kernel_and_oracle(kind, monkeypatch):
+    """>= 4096 points and >= 512 columns go through the wide kernel with two points per warp
+    (points paired by the locality permutation, shared rows of f loaded once): bit-identical to
+    the one-point-per-warp kernel and to the oracle, odd point count, ragged column remainder."""
+    rng = np.random.default_rng(77)
+    cfg = {"linear": (nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, "normal"),
+           "quadratic": (nodes_1d.cc_nodes, lambda n: np.where(n == 0, 1, 2 ** n + 1), "uniform"),
+           "cubic": (nodes_1d.equispaced_nodes, lambda n: 3 * n + 1, "normal"),
+           "lagrange": (nodes_1d.hermite_nodes, lambda n: 2 * n + 1, "normal")}
+    knots, lev, smp = cfg[kind]
+    it = SGInterpolant(mis.smolyak_mid_set(3, 5), knots, lev, tp_interpolant=KIND_CLASS[kind], verbose=False)
+    P, NF = 4611, 523
+    x = rng.normal(size=(P, 5)) if smp == "normal" else rng.uniform(-1, 1, (P, 5))
+    f = rng.normal(size=(it.num_nodes, NF))
+    got = it.interpolate(x, f)
+    monkeypatch.setenv("SGM_WIDE_PAIRS", "0")
+    one = it.interpolate(x, f)
+    monkeypatch.delenv("SGM_WIDE_PAIRS")
+    assert np.array_equal(got, one, equal_nan=True)
+    pick = np.concatenate([rng.choice(P, 40, replace=False), [P - 1]])
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[pick], f, kind, squeeze=False)
+    assert rel_err(got[pick], ref) <= TOL
+
+
 def test_term_sharding_plan_slices_on_one_gpu():
     """mode='terms' building block: evaluating contiguous term ranges with separate plans and
     adding the partial results reproduces the full interpolant to rounding."""
