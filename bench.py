@@ -36,8 +36,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of the evaluation kernel from the committed ncu capture
-# (136.03 MB read + 4.23 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
-NCU_TRAFFIC = {("c2", 10 ** 6): 140259584}
+# (135.52 MB read + 5.13 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
+NCU_TRAFFIC = {("c2", 10 ** 6): 140644096}
 
 METRIC = "interpolant point-evals x outputs per second (fp64)"
 UNIT = "point-evals*outputs/s"
@@ -399,18 +399,18 @@ def main():
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P)),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the "
                          "kernel, ncu --set full capture of this command "
-                         "(profiles/r1_v4_prefix_ncu_full.txt)",
+                         "(profiles/r1_v5_prefix_ppl2_ncu_full.txt)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel": "sgm::eval_points_prefix_kernel<8 warps, 64-term chunks, balanced "
-                                   "runs> (+ pregather and the point locality sort, <1% of the "
-                                   "step; profiles/r1_v4_launches.csv)",
+                                   "runs, 2 points per lane> (+ pregather and the point locality "
+                                   "sort, <1% of the step; profiles/r1_v5_launches.csv)",
                          "kernel_ms": kernel_ms,
                          "note": "the exact combination form is bound by the SM's L1 data pipe "
                                  "(128 B/clk/SM; 8-byte corner gathers + bracket tables) and "
                                  "FP64 issue, not HBM (DESIGN.md section 5); ncu of this kernel: "
-                                 "L1 data pipe 71 %, issue 57 %, FP64 pipe 35 % of peak "
-                                 "(profiles/r1_v4_prefix_ncu_full.txt)",
+                                 "L1 data pipe 68 %, issue 46 %, FP64 pipe 38 % of peak "
+                                 "(profiles/r1_v5_prefix_ppl2_ncu_full.txt)",
                          "corner_gathers_per_s": P * corners / (kernel_ms * 1e-3),
                          "secondary": secondary_rooflines(P, corners, len(it._coeffs),
                                                           kernel_ms, clocks.summary())},
@@ -438,6 +438,32 @@ def main():
                             "includes the GPU hierarchisation of the nodal values; best of 5"}
             except NotImplementedError as exc:
                 line["hierarchical_mode"] = {"unavailable": str(exc)}
+        if world == 1:
+            # the HBM-bound kernel of the same path family: batched
+            # Levy-Ciesielski map of config 3's parameter vectors, bytes = 8 P d + 8 nt + 8 P nt
+            from sgmethods_b200.parametric_expansions_brownian_motion import lc_brownian_device
+            Pl, dl, ntl = 10 ** 5, 64, 10 ** 3
+            yy = torch.randn((Pl, dl), dtype=torch.float64, device=dev, generator=gen)
+            tt = torch.linspace(0, 1, ntl, dtype=torch.float64, device=dev)
+            Wl = torch.empty((Pl, ntl), dtype=torch.float64, device=dev)
+            for _ in range(3):
+                lc_brownian_device(tt, yy, 1.0, Wl)
+            lts = []
+            for i in range(7):
+                flush.fill_(float(i))
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); lc_brownian_device(tt, yy, 1.0, Wl); b.record()
+                torch.cuda.synchronize()
+                lts.append(a.elapsed_time(b))
+            lms = float(np.median(lts))
+            lbytes = 8 * Pl * dl + 8 * ntl + 8 * Pl * ntl
+            line["hbm_bound_kernel"] = {
+                "kernel": "sgm::lc_brownian_tiles_kernel (Levy-Ciesielski expansion, d=64, 10^5 "
+                          "parameter vectors x 10^3 times)",
+                "ms": lms, "algorithmic_bytes": lbytes, "achieved": lbytes / lms / 1e6, "peak": peak,
+                "unit": "GB/s", "frac": lbytes / lms / 1e6 / peak,
+                "note": "not the headline workload: shows the HBM fraction of the path's "
+                        "HBM-bound kernel next to the gather-bound evaluation kernel"}
         if gather_ms is not None:
             line["final_all_gather"] = {"ms": gather_ms, "bytes_per_rank": int(P * NF * 8),
                                         "backend": "nccl all_gather_into_tensor",
