@@ -405,8 +405,9 @@ int launch_cols_wide(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, co
 // the same rows of f.  Returns SGM_OK with *launched = false when the shape does not fit.
 template <int KIND, int CPL2>
 int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
-                      int64_t ldf, int64_t n_tiles, double* out, int64_t ldo, double scale,
-                      int accumulate, const int* perm, cudaStream_t stream, bool* launched) {
+                      int64_t ldf, int64_t n_tiles, int64_t ncols, double* out, int64_t ldo,
+                      double scale, int accumulate, const int* perm, cudaStream_t stream,
+                      bool* launched) {
     *launched = false;
     const PlanDev& d = plan->dev;
     const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
@@ -420,7 +421,7 @@ int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, c
     auto kern = sgm::eval_cols_wide2_kernel<KIND, CPL2>;
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
-        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, pairs_per_block, perm);
+        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, pairs_per_block, perm, ncols);
     SGM_CUDA(cudaGetLastError());
     *launched = true;
     return SGM_OK;
@@ -445,10 +446,22 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
         const int64_t n_tiles = NF / tile;
         const char* pairs = std::getenv("SGM_WIDE_PAIRS");     // dev knob: 0 | 1
         bool launched = false;
-        if (tile == 256 && perm && !(pairs && pairs[0] == '0')) {
-            int rc2 = launch_cols_wide2<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale,
-                                                 accumulate, perm, stream, &launched);
+        if (perm && !(pairs && pairs[0] == '0')) {
+            // the pair kernel guards its last tile: all (even many) columns in one launch,
+            // an odd last column through the guarded narrow kernel
+            const int64_t even = NF & ~(int64_t)1;
+            const int64_t nt2 = (even + tile - 1) / tile;
+            int rc2 = tile == 256
+                ? launch_cols_wide2<KIND, 4>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched)
+                : tile == 128
+                ? launch_cols_wide2<KIND, 2>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched)
+                : launch_cols_wide2<KIND, 1>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched);
             if (rc2) return rc2;
+            if (launched) {
+                if (even == NF) return SGM_OK;
+                return launch_cols_narrow<KIND>(plan, x, P, ldx, f + even, ldf, 1, out + even, ldo,
+                                                scale, accumulate, stream);
+            }
         }
         int rc = launched ? SGM_OK : tile == 256
             ? launch_cols_wide<KIND, 4>(plan, x, P, ldx, f, ldf, n_tiles, out, ldo, scale, accumulate, stream)
@@ -518,7 +531,7 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         // behind the G area, shared with the scalar path: launches are ordered on the stream)
         const int* perm = nullptr;
         const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
-        if (ncols >= 512 && workspace && workspace_bytes > g_bytes + sort_scratch_bytes(P)) {
+        if (ncols >= 64 && workspace && workspace_bytes > g_bytes + sort_scratch_bytes(P)) {
             int rc = locality_sort(plan, x, P, ldx, static_cast<unsigned char*>(workspace) + g_bytes,
                                    workspace_bytes - g_bytes, stream, &perm, kSortMinPointsCols);
             if (rc) return rc;
@@ -546,6 +559,28 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (ldf % 2 == 0) && (ldo % 2 == 0);
     int64_t done = 0;
+    {   // Wide outputs on enough points: ONE launch of the two-points-per-warp kernel covers
+        // all columns (its last 256-column tile is guarded), instead of full tiles + a ragged
+        // remainder through the narrower kernels (config 4, NF = 1000: 84 -> 67 ms).  A short
+        // tail of a packed pw-linear plan still goes column by column through the scalar kernel.
+        const char* pairs = std::getenv("SGM_WIDE_PAIRS");     // dev knob: 0 | 1
+        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        const bool pairs_ok = aligned && plan->dev.n_corners > 0 && NF >= 512 && P >= kSortMinPointsCols &&
+                              P < 0x7fffffff && plan->dev.n_key >= 4 && !std::getenv("SGM_NO_SORT") &&
+                              !(pairs && pairs[0] == '0') && workspace &&
+                              workspace_bytes > g_bytes + sort_scratch_bytes(P);
+        if (pairs_ok) {
+            const int64_t tail = NF % 256;
+            const int64_t main_cols = (fast_scalar && tail <= 48) ? NF - tail : NF;
+            int rc = column_kernels(f, out, main_cols);
+            if (rc) return rc;
+            for (int64_t c = main_cols; c < NF; ++c) {
+                rc = scalar_column(c);
+                if (rc) return rc;
+            }
+            return SGM_OK;
+        }
+    }
     if (wide_cols && aligned && plan->dev.n_corners > 0) {
         int rc = column_kernels(f, out, wide_cols);
         if (rc) return rc;

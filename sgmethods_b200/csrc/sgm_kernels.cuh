@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(256, 2)
 eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                        const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
                        int64_t ldo, double scale, int accumulate, int pairs_per_block,
-                       const int* __restrict__ perm) {
+                       const int* __restrict__ perm, int64_t ncols) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1214,6 +1214,11 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
     // lane owns columns tile*64*CPL2 + 64*c + 2*lane + {0, 1}, c < CPL2
     const int64_t col0 = (int64_t)blockIdx.y * (64 * CPL2) + 2 * lane;
     const double* fcol = f + col0;
+    // the last tile may be ragged: column pairs at or beyond ncols (even) are neither read
+    // nor written
+    bool okc[CPL2];
+#pragma unroll
+    for (int c = 0; c < CPL2; ++c) okc[c] = col0 + 64 * c + 1 < ncols;
     const int64_t n_pairs = (P + 1) >> 1;
     const int64_t q_begin = (int64_t)blockIdx.x * pairs_per_block;
     const int64_t q_end = min(n_pairs, q_begin + pairs_per_block);
@@ -1281,7 +1286,7 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
                 double2 v[CPL2];
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c)
-                    v[c] = __ldg(reinterpret_cast<const double2*>(frA + 64 * c));
+                    v[c] = okc[c] ? __ldg(reinterpret_cast<const double2*>(frA + 64 * c)) : make_double2(0.0, 0.0);
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c) {
                     tpA[c].x = tpA[c].x + v[c].x * wvA;
@@ -1291,7 +1296,7 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
                     const double* frB = fcol + (int64_t)rB * ldf;
 #pragma unroll
                     for (int c = 0; c < CPL2; ++c)
-                        v[c] = __ldg(reinterpret_cast<const double2*>(frB + 64 * c));
+                        v[c] = okc[c] ? __ldg(reinterpret_cast<const double2*>(frB + 64 * c)) : make_double2(0.0, 0.0);
                 }
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c) {
@@ -1318,6 +1323,7 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
             double* o = out + (pt == 0 ? pA : pB) * ldo + col0;
 #pragma unroll
             for (int c = 0; c < CPL2; ++c) {
+                if (!okc[c]) continue;
                 double2* dst = reinterpret_cast<double2*>(o + 64 * c);
                 const double2 a2 = pt == 0 ? accA[c] : accB[c];
                 double2 r = make_double2(scale * a2.x, scale * a2.y);

@@ -321,6 +321,26 @@ def test_levy_ciesielski_large_batch_against_oracle():
         assert np.array_equal(W[p], brownian_oracle.lc_brownian(tt, yy[p], 1.0))
 
 
+@pytest.mark.parametrize("d", [3, 5, 48, 100, 150, 200])
+def test_levy_ciesielski_ragged_shapes_against_oracle(d):
+    """Staging paths of the tiled kernel: coefficient counts that do not divide the block size
+    (row/column carry of the cp.async copy), more than 6 levels, shared memory above 48 KB
+    (d = 150), the generic kernel (d = 200), several row groups with a ragged last group,
+    a strided view of the parameter vectors, a time grid that is not a multiple of the tile."""
+    import torch
+    rng = np.random.default_rng(300 + d)
+    P, nt = 77, 700
+    tt = np.sort(rng.uniform(0, 2.0, nt))
+    tt[0], tt[-1] = 0.0, 2.0
+    big = rng.normal(size=(P, d + 3))
+    y_view = torch.from_numpy(big).cuda()[:, 1:d + 1]           # leading dimension d + 3
+    from sgmethods_b200.parametric_expansions_brownian_motion import lc_brownian_device
+    W = lc_brownian_device(torch.from_numpy(tt).cuda(), y_view, 2.0).cpu().numpy()
+    assert W.shape == (P, nt) and not y_view.is_contiguous()
+    for p in (0, 31, 32, 63, 64, 76):
+        assert np.array_equal(W[p], brownian_oracle.lc_brownian(tt, big[p, 1:d + 1], 2.0)), (d, p)
+
+
 def test_karhunen_loeve_against_reference_outputs():
     g = load_golden("brownian")
     W = param_KL_Brownian_motion(g["kl_tt"], g["kl_yy"])
@@ -486,8 +506,9 @@ def test_vector_outputs_across_column_tile_boundaries():
     assert np.array_equal(got.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("NF", [523, 457])
 @pytest.mark.parametrize("kind", ["linear", "quadratic", "cubic", "lagrange"])
-def test_two_points_per_warp_wide_kernel_equals_one_point_kernel_and_oracle(kind, monkeypatch):
+def test_two_points_per_warp_wide_kernel_equals_one_point_kernel_and_oracle(kind, NF, monkeypatch):
     """>= 4096 points and >= 512 columns go through the wide kernel with two points per warp
     (points paired by the locality permutation, shared rows of f loaded once): bit-identical to
     the one-point-per-warp kernel and to the oracle, odd point count, ragged column remainder."""
@@ -498,7 +519,7 @@ def test_two_points_per_warp_wide_kernel_equals_one_point_kernel_and_oracle(kind
            "lagrange": (nodes_1d.hermite_nodes, lambda n: 2 * n + 1, "normal")}
     knots, lev, smp = cfg[kind]
     it = SGInterpolant(mis.smolyak_mid_set(3, 5), knots, lev, tp_interpolant=KIND_CLASS[kind], verbose=False)
-    P, NF = 4611, 523
+    P = 4611                                        # NF = 457: 128- and 64-column tiles
     x = rng.normal(size=(P, 5)) if smp == "normal" else rng.uniform(-1, 1, (P, 5))
     f = rng.normal(size=(it.num_nodes, NF))
     got = it.interpolate(x, f)
