@@ -411,9 +411,9 @@ int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, c
     *launched = false;
     const PlanDev& d = plan->dev;
     const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
-    const size_t per_warp = 2 * ((size_t)d.B * 8 + (size_t)d.E * 4);
+    const size_t per_warp = 2 * ((size_t)d.B * 8 + (size_t)d.E * 4) + 32 * (16 + 8 + 8);   // + entry staging
     const int warps = 8;
-    const size_t smem = fixed + per_warp * warps;
+    const size_t smem = fixed + per_warp * warps + 16;              // + alignment of the staging area
     if (smem > (size_t)plan->max_smem_optin / 2) return SGM_OK;    // keep two blocks per SM
     const int pairs_per_block = warps * 4;
     const int64_t gx = ((P + 1) / 2 + pairs_per_block - 1) / pairs_per_block;

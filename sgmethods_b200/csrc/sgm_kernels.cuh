@@ -1207,7 +1207,15 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
     double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* basA = sbas_all + (size_t)(2 * warp) * pl.B;
     double* basB = basA + pl.B;
-    int* idxA = reinterpret_cast<int*>(sbas_all + (size_t)(2 * n_warps) * pl.B) + (size_t)(2 * warp) * pl.E;
+    // per-warp staging of 32 list entries: (wA, wB) | (rowA + last flag, rowB) | coefficient;
+    // written once per batch by the lane that set the entry up, read back as broadcasts
+    // (3 shared-memory wavefronts per entry instead of 7 warp shuffles)
+    unsigned char* stage = reinterpret_cast<unsigned char*>(sbas_all + (size_t)(2 * n_warps) * pl.B);
+    stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;      // 16-byte entries
+    double2* sW = reinterpret_cast<double2*>(stage) + (size_t)warp * 32;
+    double* sC = reinterpret_cast<double*>(stage + (size_t)n_warps * 32 * 16) + (size_t)warp * 32;
+    int2* sR = reinterpret_cast<int2*>(stage + (size_t)n_warps * 32 * 24) + (size_t)warp * 32;
+    int* idxA = reinterpret_cast<int*>(stage + (size_t)n_warps * 32 * 32) + (size_t)(2 * warp) * pl.E;
     int* idxB = idxA + pl.E;
     __syncthreads();
 
@@ -1275,13 +1283,18 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
                 last = (cid == h.ncorner - 1);
                 if (last) coef = pl.coeff[t];
             }
+            __syncwarp();                                        // previous batch fully read
+            sW[lane] = make_double2(wA, wB);
+            sR[lane] = make_int2(rowA | (last << 31), rowB);
+            sC[lane] = coef;
+            __syncwarp();
             const int n_in = min(32, pl.n_corners - g0);
             for (int cc = 0; cc < n_in; ++cc) {
-                const double wvA = __shfl_sync(0xffffffffu, wA, cc);
-                const double wvB = __shfl_sync(0xffffffffu, wB, cc);
-                const int rA = __shfl_sync(0xffffffffu, rowA, cc);
-                const int rB = __shfl_sync(0xffffffffu, rowB, cc);
-                const int is_last = __shfl_sync(0xffffffffu, last, cc);
+                const double2 wv = sW[cc];
+                const int2 rr = sR[cc];
+                const double wvA = wv.x, wvB = wv.y;
+                const int rA = rr.x & 0x7fffffff, rB = rr.y;
+                const int is_last = rr.x < 0;
                 const double* frA = fcol + (int64_t)rA * ldf;
                 double2 v[CPL2];
 #pragma unroll
@@ -1304,7 +1317,7 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
                     tpB[c].y = tpB[c].y + v[c].y * wvB;
                 }
                 if (is_last) {
-                    const double cf = __shfl_sync(0xffffffffu, coef, cc);
+                    const double cf = sC[cc];
 #pragma unroll
                     for (int c = 0; c < CPL2; ++c) {
                         accA[c].x = accA[c].x + cf * tpA[c].x;
