@@ -231,6 +231,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line only: keep a private handle on it and point file
+    # descriptor 1 at stderr, so that whatever libraries write to stdout (NCCL prints its
+    # version line there) cannot end up next to the result
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         if rank != 0:
@@ -261,7 +267,7 @@ def main():
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "wall_s": total}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     import torch
@@ -272,8 +278,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's version / debug lines go to stderr: stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     it, desc, P_default, NF, sampler = build_workload(args.workload)
@@ -479,7 +483,7 @@ def main():
             v1, dt1 = cpu_single_core_rate(it, KIND_NAME[it._kind], NF, 1024, sampler)
             line["cpu_baseline"]["single_core"] = {"value": v1, "cores": 1,
                                                    "sample": f"1024 points, 1 process ({dt1:.1f} s)"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -14,6 +14,9 @@ from sgmethods_b200 import multi_index_sets as mis, nodes_1d
 from sgmethods_b200.distributed import ShardedInterpolant, shard_bounds
 from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
 
+sys.stdout.flush()
+json_out = os.fdopen(os.dup(1), "w")      # stdout = the JSON line only (NCCL prints to fd 1)
+os.dup2(2, 1)
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -69,6 +72,6 @@ if rank == 0:
                       "eval_s_max_over_ranks": float(t[0]), "all_gather_s": float(t[1]),
                       "wall_s_incl_point_generation": float(t[2]),
                       "point_evals_per_s": P_total / float(t[0]),
-                      "partition_of_unity_max_dev": unity}), flush=True)
+                      "partition_of_unity_max_dev": unity}), file=json_out, flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
