@@ -1187,12 +1187,12 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
 // own registers, in the same order as when evaluated alone -- bit-identical).  This halves
 // the L1 -> register traffic that bounds the wide kernel for every shared row and doubles the
 // FP64 work in flight per load.
-template <int KIND, int CPL2>
-__global__ void __launch_bounds__(256, 2)
-eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
-                       const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
-                       int64_t ldo, double scale, int accumulate, int pairs_per_block,
-                       const int* __restrict__ perm, int64_t ncols) {
+template <int KIND, int CPL2, bool GUARD>
+__device__ __forceinline__ void
+cols_wide2_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                int64_t ldo, double scale, int accumulate, int pairs_per_block,
+                const int* __restrict__ perm, int64_t ncols) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1222,11 +1222,11 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
     // lane owns columns tile*64*CPL2 + 64*c + 2*lane + {0, 1}, c < CPL2
     const int64_t col0 = (int64_t)blockIdx.y * (64 * CPL2) + 2 * lane;
     const double* fcol = f + col0;
-    // the last tile may be ragged: column pairs at or beyond ncols (even) are neither read
-    // nor written
+    // GUARD (ragged last tile only): column pairs at or beyond ncols (even) are neither read
+    // nor written; full tiles run the unguarded instantiation
     bool okc[CPL2];
 #pragma unroll
-    for (int c = 0; c < CPL2; ++c) okc[c] = col0 + 64 * c + 1 < ncols;
+    for (int c = 0; c < CPL2; ++c) okc[c] = !GUARD || col0 + 64 * c + 1 < ncols;
     const int64_t n_pairs = (P + 1) >> 1;
     const int64_t q_begin = (int64_t)blockIdx.x * pairs_per_block;
     const int64_t q_end = min(n_pairs, q_begin + pairs_per_block);
@@ -1349,6 +1349,20 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
             }
         }
     }
+}
+
+template <int KIND, int CPL2>
+__global__ void __launch_bounds__(256, 2)
+eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                       const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                       int64_t ldo, double scale, int accumulate, int pairs_per_block,
+                       const int* __restrict__ perm, int64_t ncols) {
+    if (((int64_t)blockIdx.y + 1) * (64 * CPL2) <= ncols)        // block-uniform
+        cols_wide2_body<KIND, CPL2, false>(pl, x, P, ldx, f, ldf, out, ldo, scale, accumulate,
+                                           pairs_per_block, perm, ncols);
+    else
+        cols_wide2_body<KIND, CPL2, true>(pl, x, P, ldx, f, ldf, out, ldo, scale, accumulate,
+                                          pairs_per_block, perm, ncols);
 }
 
 // One batch of the dimension-wise hierarchisation (surplus = value - coarser interpolant).

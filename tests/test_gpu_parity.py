@@ -226,13 +226,17 @@ def test_config4_shape_multilevel_quadratic_nf1000_against_oracle():
     rng = np.random.default_rng(41)
     NF = 1000
     ml = [rng.normal(size=(seq[3 - k].num_nodes, NF)) for k in range(4)]
-    yy = rng.uniform(-1, 1, (2500, 8))
-    got = MLInterpolant(seq).interpolate(yy, ml)
     plans = [oracle_plan_of(it) for it in seq]
     for p, it in zip(plans, seq):
         p.SG = it.SG
-    ref = drivers_oracle.ml_interpolate(plans, "quadratic", yy[:64], ml)
-    assert rel_err(got[:64], ref) <= TOL
+    # 2500 points: one point per warp; 4500 points: the accumulating (+I_k, -I_{k-1}) launches go
+    # through the two-points-per-warp kernel with its guarded last column tile
+    for P in (2500, 4500):
+        yy = rng.uniform(-1, 1, (P, 8))
+        got = MLInterpolant(seq).interpolate(yy, ml)
+        pick = np.concatenate([np.arange(48), [P - 2, P - 1]])
+        ref = drivers_oracle.ml_interpolate(plans, "quadratic", yy[pick], ml)
+        assert rel_err(got[pick], ref) <= TOL
 
 
 def test_torch_tensors_in_torch_tensor_out_and_extra_columns():
