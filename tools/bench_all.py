@@ -125,6 +125,24 @@ for w in which:
         print(json.dumps({"case": "c4 multilevel 4 levels pw-quadratic NF=1e3 (fused signed sum)",
                           "P": P, "NF": NF, "ms": ms, "evals_per_s": P * NF / ms * 1e3,
                           "hbm_gbs": (8 * P * 8 + 8 * P * NF) / ms / 1e6}), flush=True)
+    elif w == "c3full":       # BASELINE config 3 at its full size: 10^5 points x 10^4 outputs
+        a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
+        it = SGInterpolant(mis.aniso_smolyak_mid_set(10, 64, a),
+                           lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2), l2, verbose=False)
+        run_interp("c3 FULL SIZE LC-aniso d=64 w=10 pw-linear", it, 10 ** 5, 10 ** 4, reps=2)
+    elif w == "c4full":       # BASELINE config 4 at its full size: 4 levels, 10^6 points x 10^3 outputs
+        seq = [SGInterpolant(mis.smolyak_mid_set(k, 8), nodes_1d.cc_nodes, dbl,
+                             tp_interpolant=TPPwQuadraticInterpolator, verbose=False) for k in range(4)]
+        mli = MLInterpolant(seq)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        P, NF = 10 ** 6, 10 ** 3
+        yy = torch.rand((P, 8), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        ml = [torch.randn((seq[3 - k].num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
+              for k in range(4)]
+        ms = timed(lambda: mli.interpolate(yy, ml), 2, 1)
+        print(json.dumps({"case": "c4 FULL SIZE multilevel 4 levels pw-quadratic NF=1e3 (fused signed sum)",
+                          "P": P, "NF": NF, "ms": ms, "evals_per_s": P * NF / ms * 1e3,
+                          "hbm_gbs": (8 * P * 8 + 8 * P * NF) / ms / 1e6}), flush=True)
     elif w == "lc":
         for P, d, nt in ((10 ** 5, 64, 10 ** 3), (10 ** 4, 64, 10 ** 4)):
             gen = torch.Generator(device=dev).manual_seed(0)
