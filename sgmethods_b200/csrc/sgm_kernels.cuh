@@ -1422,12 +1422,16 @@ __global__ void lc_brownian_kernel(const double* __restrict__ tt, int64_t nt,
 // L x (load y_k, two multiplies, one add) and one store; a block writes 2*TPT KB of every row
 // contiguously, which keeps the HBM write stream page-friendly.
 constexpr int LC_ROWS = 32;
-template <int LMAX, int TPT, int BPS>
+// DC: number of coefficients when known at compile time (64 = config 3), 0 = run-time `d_rt`:
+// with a constant row length all staging index arithmetic folds away and the coefficient
+// reads of the unrolled row loop address as per-thread register + immediate.
+template <int LMAX, int TPT, int BPS, int DC = 0>
 __global__ void __launch_bounds__(256, BPS)
 lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
-                         const double* __restrict__ yy, int64_t P, int d, int64_t ldy, double T,
+                         const double* __restrict__ yy, int64_t P, int d_rt, int64_t ldy, double T,
                          double sqrtT, const double* __restrict__ level_scale, int L,
                          double* __restrict__ W, int64_t ldw, int rows_per_block) {
+    const int d = DC ? DC : d_rt;
     const int64_t t_base = (int64_t)blockIdx.x * (256 * TPT) + threadIdx.x;
     int kidx[TPT][LMAX];
     double eta[TPT][LMAX], sv[TPT];
@@ -1506,17 +1510,19 @@ lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
         }
         __syncthreads();     // group g visible to all; everybody is done with group g - 1
         if (pb + LC_ROWS < p1) issue_copy(pb + LC_ROWS, (g + 1) & 1);
-        for (int r = 0; r < nrows; ++r) {
-            const double* y = buf + (size_t)r * d;
+        // row pointers advance by uniform increments (shared-memory reads address as
+        // per-thread offset + uniform row base, stores as per-thread column + uniform row)
+        const double* y = buf;
+        double* wrow = W + pb * ldw + t_base;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r, y += d, wrow += ldw) {
             const double y0 = y[0];
-            double* wrow = W + (pb + r) * ldw;
 #pragma unroll
             for (int q = 0; q < TPT; ++q) {
                 double w = y0 * sv[q];
 #pragma unroll
                 for (int l = 0; l < LMAX; ++l) w = w + y[kidx[q][l]] * eta[q][l];
-                const int64_t it = t_base + q * 256;
-                if (it < nt) wrow[it] = w * sqrtT;
+                if (t_base + q * 256 < nt) wrow[q * 256] = w * sqrtT;
             }
         }
     }
