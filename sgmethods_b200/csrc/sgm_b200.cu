@@ -1057,10 +1057,25 @@ int sgm_kl_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
     int dev = 0, sms = 148;
     SGM_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t total = P * nt;
-    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
-    sgm::kl_brownian_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        tt, nt, yy, P, d, ldy, factor, freq, W, ldw);
+    const size_t kl_smem = ((size_t)d * sgm::KL_TT + (size_t)sgm::KL_ROWS * d) * 8;
+    if (d >= 1 && P >= 64 && kl_smem <= 96 * 1024 && !std::getenv("SGM_KL_PER_OUTPUT")) {   // (dev knob)
+        // tiled kernel: sines once per (block, time), rows streamed through shared memory
+        const int64_t gx = (nt + sgm::KL_TT - 1) / sgm::KL_TT;
+        int64_t rows = std::max<int64_t>(256, (P * gx + (int64_t)sms * 8 - 1) / ((int64_t)sms * 8));
+        int64_t gy = (P + rows - 1) / rows;
+        if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
+        if (kl_smem > 48 * 1024)
+            SGM_CUDA(cudaFuncSetAttribute(sgm::kl_brownian_tiles_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kl_smem));
+        sgm::kl_brownian_tiles_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, kl_smem,
+                                        static_cast<cudaStream_t>(stream)>>>(
+            tt, nt, yy, P, d, ldy, factor, freq, W, ldw, (int)rows);
+    } else {
+        const int64_t total = P * nt;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+        sgm::kl_brownian_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            tt, nt, yy, P, d, ldy, factor, freq, W, ldw);
+    }
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }

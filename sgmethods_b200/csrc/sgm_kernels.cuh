@@ -1545,4 +1545,53 @@ __global__ void kl_brownian_kernel(const double* __restrict__ tt, int64_t nt,
     }
 }
 
+// Tiled form: the factor  a_n(t) = factor_n * sin(freq_n * t)  does not depend on the
+// parameter vector, so a block computes it ONCE for its 64 times (shared memory, [n][64])
+// and then streams over its rows, which are staged 32 at a time.  Thread = (time, row lane):
+// 64 times x 4 row lanes; a thread evaluates two rows at once, so one read of a_n(t) serves
+// two outputs.  Per output: d x (product, sum) in the order of the reference
+// (parametric_expansions_brownian_motion.py:88-91), d sines per block instead of per output.
+constexpr int KL_TT = 64, KL_ROWS = 32;
+__global__ void __launch_bounds__(256)
+kl_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt, const double* __restrict__ yy,
+                         int64_t P, int d, int64_t ldy, const double* __restrict__ factor,
+                         const double* __restrict__ freq, double* __restrict__ W, int64_t ldw,
+                         int rows_per_block) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);          // [d][KL_TT]
+    double* sy = sA + (size_t)d * KL_TT;                       // [KL_ROWS][d]
+    const int tl = threadIdx.x & (KL_TT - 1), rl = threadIdx.x >> 6;
+    const int64_t t0 = (int64_t)blockIdx.x * KL_TT;
+    const int64_t it = t0 + tl;
+    const double t = it < nt ? tt[it] : 0.0;
+    for (int n = rl; n < d; n += 4) sA[n * KL_TT + tl] = factor[n] * sin(freq[n] * t);
+    const int64_t p0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t p1 = min(P, p0 + rows_per_block);
+    const double w0 = 0.0 * t;
+    for (int64_t pb = p0; pb < p1; pb += KL_ROWS) {
+        const int nrows = (int)min((int64_t)KL_ROWS, p1 - pb);
+        __syncthreads();                                         // sA ready / previous rows consumed
+        for (int i = threadIdx.x; i < nrows * d; i += 256) {
+            const int r = i / d, c = i - r * d;
+            sy[i] = __ldg(yy + (pb + r) * ldy + c);
+        }
+        __syncthreads();
+        for (int r = rl; r < nrows; r += 8) {                    // rows r and r + 4
+            const bool two = r + 4 < nrows;
+            const double* ya = sy + (size_t)r * d;
+            const double* yb = sy + (size_t)(two ? r + 4 : r) * d;
+            double wa = w0, wb = w0;
+            for (int n = 0; n < d; ++n) {
+                const double a = sA[n * KL_TT + tl];
+                wa = wa + a * ya[n];
+                wb = wb + a * yb[n];
+            }
+            if (it < nt) {
+                W[(pb + r) * ldw + it] = wa;
+                if (two) W[(pb + r + 4) * ldw + it] = wb;
+            }
+        }
+    }
+}
+
 }  // namespace sgm

@@ -9,6 +9,8 @@ Tolerance (BASELINE.json north_star): max|gpu - ref| / max|ref| <= 1e-12 in fp64
 kernels reproduce the reference's operation order, so most results are bit-identical; the
 bit-exact fraction is printed for information.
 """
+from math import pi
+
 import numpy as np
 import pytest
 
@@ -349,6 +351,24 @@ def test_karhunen_loeve_against_reference_outputs():
     g = load_golden("brownian")
     W = param_KL_Brownian_motion(g["kl_tt"], g["kl_yy"])
     assert rel_err(W, g["kl_W"]) <= TOL
+
+
+def test_karhunen_loeve_tiled_kernel_equals_per_output_kernel():
+    """>= 64 parameter vectors go through the tiled kernel (sines once per block and time,
+    rows streamed through shared memory, two rows per thread): bit-identical to the
+    one-thread-per-output kernel that small batches use; ragged rows / times, d not a
+    divisor of the block size."""
+    rng = np.random.default_rng(9)
+    for d, P, nt in ((64, 203, 130), (5, 77, 64), (100, 64, 1)):
+        tt = np.sort(rng.uniform(0, 1, nt))
+        yy = rng.normal(size=(P, d))
+        W = param_KL_Brownian_motion(tt, yy)
+        assert W.shape == (P, nt)
+        for p in (0, 3, 4, 31, 32, 36, P - 1):
+            assert np.array_equal(W[p], param_KL_Brownian_motion(tt, yy[p])), (d, p)
+        ref = np.array([[np.sum([pi * (n + 0.5) * np.sqrt(2) * np.sin((n + 0.5) * pi * t) * yy[7, n]
+                                 for n in range(d)]) for t in tt]])
+        assert rel_err(W[7:8], ref) <= 1e-11
 
 
 # ------------------------------------------------------------------ composite drivers (a12, a14)
