@@ -235,8 +235,11 @@ def main():
     # descriptor 1 at stderr, so that whatever libraries write to stdout (NCCL prints its
     # version line there) cannot end up next to the result
     sys.stdout.flush()
-    json_out = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
+    try:
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    except OSError:                       # no usable descriptors: print where print() goes
+        json_out = sys.stdout
 
     if args.impl == "reference":
         if rank != 0:
