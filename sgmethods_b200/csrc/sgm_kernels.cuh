@@ -412,8 +412,13 @@ __device__ __forceinline__ double hier_term_packed(const int4 r1, const double* 
     return At[off] * w;
 }
 
+// (an explicit minimum of one block per SM for the nested-walk kinds: without it ptxas held the
+// Lagrange instantiations at 64 registers with 224 bytes of spills inside the loop nest)
+__host__ __device__ constexpr int split_min_blocks(int kind) {
+    return (kind == SGM_PW_QUADRATIC || kind == SGM_PW_CUBIC || kind == SGM_LAGRANGE) ? 1 : 0;
+}
 template <int KIND, int W, int CHUNK>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(W * 32, split_min_blocks(KIND))
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
                          double scale, int accumulate, const int* __restrict__ perm) {
