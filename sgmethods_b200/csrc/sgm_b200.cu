@@ -54,6 +54,7 @@ struct sgm_plan {
     int prefix_wins = -1;        // cached occupancy comparison prefix vs split kernel (-1: not yet)
     int64_t table_bytes = 0;
     int kmax = 0;
+    int max_entry_n = 0;         // largest knot family among the table entries
     int sm_count = 148;
     int max_smem_optin = 0;
     std::vector<void*> allocations;
@@ -130,17 +131,23 @@ size_t sort_scratch_bytes(int64_t P) {
 }
 
 // Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
-struct SplitLaunch { int warps; int chunk; size_t smem; int blocks_per_sm; };
+struct SplitLaunch { int warps; int chunk; size_t smem; int blocks_per_sm; bool idx8; };
 
 using SplitKernel = void (*)(const PlanDev, const double*, int64_t, int64_t, const double*,
                              double*, int64_t, double, int, const int*);
 
 template <int KIND>
-SplitKernel split_kernel_for(int warps, int chunk) {
-    // 1024-thread blocks (64 registers): for plans whose bracket tables leave room for one
-    // block per SM only (config 5: 128 directions, 92 KB of tables per 32 points)
-    if constexpr (KIND == SGM_PW_LINEAR)
+SplitKernel split_kernel_for(int warps, int chunk, bool idx8 = false) {
+    if constexpr (KIND == SGM_PW_LINEAR) {
+        // byte bracket indices + 48-term chunks: two 16-warp blocks per SM where 16-bit indices
+        // and 64-term chunks allow a single block (config 5: 288 table entries)
+        if (idx8 && warps == 16 && chunk == 48) return sgm::eval_points_split_kernel<KIND, 16, 48, true>;
+        if (idx8) return nullptr;
+        // 1024-thread blocks (64 registers): for plans whose bracket tables leave room for one
+        // block per SM only (128 directions, 92 KB of tables per 32 points)
         if (warps == 32 && chunk == 128) return sgm::eval_points_split_kernel<KIND, 32, 128>;
+    }
+    if (idx8) return nullptr;
     if (warps == 16 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 16, 64>;
     if (warps == 8 && chunk == 32) return sgm::eval_points_split_kernel<KIND, 8, 32>;
     if (warps == 8 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 8, 64>;
@@ -150,24 +157,30 @@ SplitKernel split_kernel_for(int warps, int chunk) {
 template <int KIND>
 SplitLaunch choose_split_launch(const sgm_plan* plan) {
     const PlanDev& d = plan->dev;
-    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) +
-                         (size_t)d.B * 32 * 8 + (size_t)d.E * 32 * 2 + 32 * 8 + 64;
-    SplitLaunch best{0, 0, 0, 0};
+    const size_t fixed_no_idx = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) +
+                                (size_t)d.B * 32 * 8 + 32 * 8 + 64;
+    SplitLaunch best{0, 0, 0, 0, false};
     int best_warps = 0;
-    const int cand[5][2] = {{16, 64}, {8, 32}, {8, 64}, {4, 32}, {32, 128}};
+    // {warps, chunk, byte indices}; at equal resident warps the candidate with more blocks per
+    // SM wins (independent blocks overlap each other's chunk barriers)
+    const int cand[6][3] = {{16, 64, 0}, {8, 32, 0}, {8, 64, 0}, {4, 32, 0}, {32, 128, 0}, {16, 48, 1}};
+    const bool idx8_ok = KIND == SGM_PW_LINEAR && plan->all_packed && plan->max_entry_n <= 257 &&
+                         !std::getenv("SGM_NO_IDX8");            // (dev knob)
     for (const auto& c : cand) {
         if (c[0] == 32 && KIND != SGM_PW_LINEAR) continue;
-        const size_t smem = fixed + 2 * (size_t)c[1] * 32 * 8;
+        if (c[2] && !idx8_ok) continue;
+        const size_t smem = fixed_no_idx + (size_t)d.E * 32 * (c[2] ? 1 : 2) + 2 * (size_t)c[1] * 32 * 8;
         if (smem > (size_t)plan->max_smem_optin) continue;
-        SplitKernel kern = split_kernel_for<KIND>(c[0], c[1]);
+        SplitKernel kern = split_kernel_for<KIND>(c[0], c[1], c[2] != 0);
+        if (!kern) continue;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             continue;
         int bps = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, c[0] * 32, smem) != cudaSuccess)
             continue;
-        if (bps * c[0] > best_warps) {
+        if (bps * c[0] > best_warps || (bps * c[0] == best_warps && bps > best.blocks_per_sm)) {
             best_warps = bps * c[0];
-            best = SplitLaunch{c[0], c[1], smem, bps};
+            best = SplitLaunch{c[0], c[1], smem, bps, c[2] != 0};
         }
     }
     return best;
@@ -320,7 +333,7 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
             }
         }
     }
-    SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk);
+    SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk, L.idx8);
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
                                                             scale, accumulate, perm);
@@ -855,6 +868,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     plan->corners = corners;
     plan->all_packed = (n_packed == T);
     plan->kmax = kmax;
+    for (const Entry& e : entries) plan->max_entry_n = std::max(plan->max_entry_n, e.n);
     PlanDev& d = plan->dev;
     d.kind = kind; d.N = N; d.E = (int)entries.size(); d.B = B; d.T = (int)T;
     d.n_knots = (int)n_knots;

@@ -17,6 +17,7 @@
 //   term walk              sparse_grid_interpolant.py:268-279, tp_interpolant_wrapper.py:54-64
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "../../include/sgm_b200.h"
@@ -357,9 +358,9 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
 //   (1) p_t = c_t * tp_t is computed by any warp, in any order, and parked in shared memory;
 //   (2) out = out + p_t is then applied in term order by ONE warp per chunk (rotating).
 // ---------------------------------------------------------------------------------------
-template <int K>
+template <int K, typename IdxT = unsigned short>
 __device__ __forceinline__ double linear_term_packed(const int4 r1, const double* bas,
-                                                     const unsigned short* idx,
+                                                     const IdxT* idx,
                                                      const double* __restrict__ Gt) {
     // r1 = {ent0|ent1<<16, ent2|ent3<<16, stride0|stride1<<16, stride2|stride3<<16};
     // the last active direction always has stride 1 (C order).
@@ -417,12 +418,17 @@ __device__ __forceinline__ double hier_term_packed(const int4 r1, const double* 
 __host__ __device__ constexpr int split_min_blocks(int kind) {
     return (kind == SGM_PW_QUADRATIC || kind == SGM_PW_CUBIC || kind == SGM_LAGRANGE) ? 1 : 0;
 }
-template <int KIND, int W, int CHUNK>
+// IDX8 (pw-linear plans whose terms are all packed and whose knot families have <= 257 knots):
+// bracket indices are stored as bytes, which brings the tables of config 5 (288 entries) under
+// the size that lets TWO 16-warp blocks share an SM instead of one 32-warp block.
+template <int KIND, int W, int CHUNK, bool IDX8 = false>
 __global__ void __launch_bounds__(W * 32, split_min_blocks(KIND))
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
                          double scale, int accumulate, const int* __restrict__ perm) {
     constexpr int chunk = CHUNK;
+    static_assert(!IDX8 || KIND == SGM_PW_LINEAR, "byte indices: packed pw-linear plans only");
+    using IdxT = typename std::conditional<IDX8, unsigned char, unsigned short>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -437,9 +443,9 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
     double* bas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* sP = bas_all + (size_t)pl.B * 32;                 // [2][chunk][32]
     double* sOut = sP + 2 * (size_t)chunk * 32;               // [32]
-    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sOut + 32);
+    IdxT* idx_all = reinterpret_cast<IdxT*>(sOut + 32);
     const double* bas = bas_all + lane;
-    const unsigned short* idx = idx_all + lane;
+    const IdxT* idx = idx_all + lane;
     const int4* rec4 = reinterpret_cast<const int4*>(pl.rec);
 
     const int64_t n_tiles = (P + 31) >> 5;
@@ -454,8 +460,8 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
         __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
         for (int e = warp; e < pl.E; e += W) {
             const Entry en = pl.ent[e];
-            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
-                                             idx_all + lane, e, 32, pl.flags);
+            fill_basis<KIND, IdxT>(en, xp[en.dim], sknots, slambda, bas_all + lane,
+                                   idx_all + lane, e, 32, pl.flags);
         }
         __syncthreads();
         if (pl.T == 0 && warp == 0 && valid) {
@@ -474,11 +480,13 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                     const int4 r1 = __ldg(rec4 + 2 * t + 1);
                     switch (r0.w & 0xff) {
                         case 0: tp = G[r0.z]; break;
-                        case 1: tp = linear_term_packed<1>(r1, bas, idx, G + r0.z); break;
-                        case 2: tp = linear_term_packed<2>(r1, bas, idx, G + r0.z); break;
-                        case 3: tp = linear_term_packed<3>(r1, bas, idx, G + r0.z); break;
-                        default: tp = linear_term_packed<4>(r1, bas, idx, G + r0.z); break;
+                        case 1: tp = linear_term_packed<1, IdxT>(r1, bas, idx, G + r0.z); break;
+                        case 2: tp = linear_term_packed<2, IdxT>(r1, bas, idx, G + r0.z); break;
+                        case 3: tp = linear_term_packed<3, IdxT>(r1, bas, idx, G + r0.z); break;
+                        default: tp = linear_term_packed<4, IdxT>(r1, bas, idx, G + r0.z); break;
                     }
+                } else if constexpr (IDX8) {
+                    tp = 0.0;                                    // not reached: every term is packed
                 } else if (KIND == SGM_HIER_PW_LINEAR && (r0.w & TERMREC_PACKED)) {
                     const int4 r1 = __ldg(rec4 + 2 * t + 1);
                     switch (r0.w & 0xff) {
