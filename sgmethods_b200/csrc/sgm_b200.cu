@@ -1044,8 +1044,12 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
         if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
         using LcKernel = void (*)(const double*, int64_t, const double*, int64_t, int, int64_t, double,
                                   double, const double*, int, double*, int64_t, int);
+        // compile-time row length for the full dyadic sizes (d = 2^L <= 64)
         LcKernel kern = L > 6 ? sgm::lc_brownian_tiles_kernel<12, 2, 2>
-                      : d == 64 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 64> : sgm::lc_brownian_tiles_kernel<6, 2, 3>;
+                      : d == 64 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 64>
+                      : d == 32 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 32>
+                      : d == 16 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 16>
+                                : sgm::lc_brownian_tiles_kernel<6, 2, 3>;
         if (lc_smem > 48 * 1024)
             SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem));
         kern<<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(tt, nt, yy, P, d, ldy, T, sqrtT,

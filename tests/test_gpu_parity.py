@@ -327,7 +327,7 @@ def test_levy_ciesielski_large_batch_against_oracle():
         assert np.array_equal(W[p], brownian_oracle.lc_brownian(tt, yy[p], 1.0))
 
 
-@pytest.mark.parametrize("d", [3, 5, 48, 100, 150, 200])
+@pytest.mark.parametrize("d", [3, 5, 16, 32, 48, 64, 100, 150, 200])
 def test_levy_ciesielski_ragged_shapes_against_oracle(d):
     """Staging paths of the tiled kernel: coefficient counts that do not divide the block size
     (row/column carry of the cp.async copy), more than 6 levels, shared memory above 48 KB
