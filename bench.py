@@ -36,8 +36,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM bytes per launch of the evaluation kernel from the committed ncu capture
-# (135.52 MB read + 5.13 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB)
-NCU_TRAFFIC = {("c2", 10 ** 6): 140644096}
+# (136.39 MB read + 4.07 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB;
+#  ncu --set full -k regex:eval_points_prefix -s 4 -c 1 python bench.py --steps 2 --warmup 3)
+NCU_TRAFFIC = {("c2", 10 ** 6): 140461568}
 
 METRIC = "interpolant point-evals x outputs per second (fp64)"
 UNIT = "point-evals*outputs/s"
