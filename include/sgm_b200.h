@@ -129,11 +129,19 @@ typedef struct sgm_plan_desc {
     const int32_t* fam_newrank;/* SGM_HIER_PW_LINEAR only: per knot its rank among the knots
                                   that are NEW on this level, -1 for knots of the coarser
                                   level; term tables then have one entry per new-knot tuple */
+    int32_t n_seg;             /* 0: ordinary plan.  > 0: SEGMENTED plan -- the terms form n_seg
+                                  consecutive groups, each an independent small interpolant
+                                  (e.g. the hierarchical surplus of one refinement candidate);
+                                  evaluated by sgm_eval_segments / sgm_surplus_norms only     */
+    const int64_t* seg_off;    /* n_seg+1 term offsets, seg_off[0] = 0, seg_off[n_seg] = T    */
 } sgm_plan_desc;
 
 typedef struct sgm_plan sgm_plan;
 int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out);
 void sgm_plan_destroy(sgm_plan* plan);
+/* Re-reads the SGM_* development switches from the environment; they are
+ * otherwise read once, when the plan is created.  For tests and experiment scripts. */
+int sgm_plan_reload_knobs(sgm_plan* plan);
 /* Bytes of packed tables resident on the device / walked once per launch. */
 int64_t sgm_plan_table_bytes(const sgm_plan* plan);
 /* sum_t C_t = corner (or node) contributions per point and output: 2^k, 3^k, 4^k or S_t. */
@@ -156,6 +164,28 @@ int sgm_eval(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
              const double* f, int64_t M, int64_t NF, int64_t ldf,
              double* out, int64_t ldo, void* workspace, size_t workspace_bytes,
              void* stream);
+
+/* Batched evaluation of a SEGMENTED plan: for every segment s (a consecutive group of terms)
+ *   out[s * seg_stride + p * ldo + c] = sum_{t in segment s} c_t * TP_t(x[p])[c]
+ * in ONE launch: the bracket tables of a point are built once for all segments.  Replaces the
+ * candidate loop of compute_GG_indicators_RM (sgmethods/compute_error_indicators.py:109-120:
+ * per reduced-margin index a new SGInterpolant, its sampling and a full interpolate) by the
+ * hierarchical surpluses Delta_nu u = sum_{e <= supp nu} (-1)^{|e|} TP_{nu-e}[u] of all
+ * candidates, 2^{|supp nu|} terms each.  seg_stride >= (P-1)*ldo + NF. */
+int sgm_eval_segments(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
+                      const double* f, int64_t M, int64_t NF, int64_t ldf,
+                      double* out, int64_t ldo, int64_t seg_stride,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* sumsq[s] = sum_{p < P, c < NF} vals[s * seg_stride + p * ld + c]^2, fixed summation order. */
+int sgm_segment_sumsq(const double* vals, int32_t n_seg, int64_t P, int64_t NF, int64_t ld,
+                      int64_t seg_stride, double* sumsq, void* stream);
+/* Both steps with the surpluses kept in the caller's workspace (never copied to the host):
+ * sumsq[s] = sum_p |Delta_s u(x_p)|^2, i.e. P times the squared Monte-Carlo L2 norm the
+ * reference's indicator callback computes (compute_error_indicators.py:119). */
+size_t sgm_surplus_norms_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF);
+int sgm_surplus_norms(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
+                      const double* f, int64_t M, int64_t NF, int64_t ldf, double* sumsq,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Multilevel combination (reference: MLInterpolant.interpolate / get_ml_terms,
  * sgmethods/multilevel_interpolant.py:89-150): for n_parts plans sharing the points x,

@@ -2,6 +2,7 @@
 all arithmetic runs in the kernels of libsgm_b200.so.  There is no CPU fallback: every
 function here raises if CUDA is unavailable."""
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -29,13 +30,25 @@ def lagrange_lambdas(g):
     return 1 / lam
 
 
+_LIVE_PLANS = weakref.WeakSet()
+
+
+def reload_knobs():
+    """Re-read the SGM_* development switches for every live plan (they are read once, at plan
+    creation).  For tests and the experiment scripts under tools/."""
+    for plan in list(_LIVE_PLANS):
+        if getattr(plan, "_h", None):
+            _lib.check(_lib.load().sgm_plan_reload_knobs(plan._h))
+
+
 class DevicePlan:
     """Packed tables of one interpolant resident on one GPU (sgm_plan)."""
 
     def __init__(self, kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
-                 device=None, fam_newrank=None):
+                 device=None, fam_newrank=None, seg_off=None):
         """term_fam: (T, N) knot-family index per direction, -1 where the term has one node;
-        fam_off / fam_knots: CSR list of the families' ascending knot vectors."""
+        fam_off / fam_knots: CSR list of the families' ascending knot vectors; seg_off: term
+        offsets of the segments of a segmented plan (``eval_segments`` / ``surplus_norms``)."""
         torch = torch_cuda()
         lib = _lib.load()
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -54,6 +67,8 @@ class DevicePlan:
         # (named so that it outlives the ctypes call below)
         newrank = None if fam_newrank is None else np.ascontiguousarray(fam_newrank, dtype=np.int32)
         self.T = coeffs.shape[0]
+        seg = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int64)
+        self.n_seg = 0 if seg is None else seg.size - 1
         desc = _lib.PlanDesc(
             kind=self.kind, N=self.N, T=self.T, M=self.M,
             coeffs=_lib.ptr(coeffs, _lib.c_f64), term_fam=_lib.ptr(term_fam, _lib.c_i32),
@@ -61,22 +76,29 @@ class DevicePlan:
             n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
             fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
             fam_lambda=_lib.ptr(lam, _lib.c_f64),
-            fam_newrank=_lib.ptr(newrank, _lib.c_i32))
+            fam_newrank=_lib.ptr(newrank, _lib.c_i32),
+            n_seg=self.n_seg, seg_off=_lib.ptr(seg, _lib.c_i64))
         handle = _lib.c_vp()
         _lib.check(lib.sgm_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
         self._h = handle
         self.table_bytes = int(lib.sgm_plan_table_bytes(handle))
         self.corners_per_point = int(lib.sgm_plan_corners_per_point(handle))
-        self._workspace = None
+        self._workspaces = {}
+        _LIVE_PLANS.add(self)
 
     # -- evaluation -------------------------------------------------------------------------
-    def workspace(self, P, NF):
+    def workspace(self, P, NF, need=None):
+        """Scratch for one launch; one buffer per CUDA stream, so that launches of the same
+        plan on different streams never share scratch."""
         torch = torch_cuda()
-        need = int(_lib.load().sgm_eval_workspace_bytes(self._h, P, NF))
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8,
-                                          device=torch.device("cuda", self.device))
-        return self._workspace
+        if need is None:
+            need = int(_lib.load().sgm_eval_workspace_bytes(self._h, P, NF))
+        dev = torch.device("cuda", self.device)
+        key = torch.cuda.current_stream(dev).cuda_stream
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._workspaces[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws
 
     def eval(self, x, f, out=None):
         """x (P, >=N), f (M, NF), both fp64 CUDA tensors on this plan's device -> (P, NF)."""
@@ -97,6 +119,51 @@ class DevicePlan:
             out.data_ptr(), out.stride(0) if P > 1 else max(NF, 1), ws.data_ptr(), ws.numel(),
             stream))
         return out
+
+    def _check_inputs(self, x, f):
+        torch = torch_cuda()
+        assert x.is_cuda and f.is_cuda and x.dtype == torch.float64 and f.dtype == torch.float64
+        assert x.dim() == 2 and f.dim() == 2
+        assert (x.shape[1] == 1 or x.stride(1) == 1) and (f.shape[1] == 1 or f.stride(1) == 1)
+
+    def eval_segments(self, x, f, out=None):
+        """Segmented plan: (n_seg, P, NF) tensor, out[s] = sum over the terms of segment s
+        (sgm_eval_segments, one launch for all segments)."""
+        torch = torch_cuda()
+        self._check_inputs(x, f)
+        P, NF = x.shape[0], f.shape[1]
+        if out is None:
+            out = torch.empty((self.n_seg, P, NF), dtype=torch.float64, device=x.device)
+        if P == 0 or self.n_seg == 0:
+            return out
+        ws = self.workspace(P, NF)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().sgm_eval_segments(
+            self._h, x.data_ptr(), P, x.stride(0) if P > 1 else max(x.shape[1], 1),
+            f.data_ptr(), f.shape[0], NF, f.stride(0) if f.shape[0] > 1 else max(NF, 1),
+            out.data_ptr(), NF, P * NF, ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def surplus_sumsq(self, x, f):
+        """Segmented plan: (n_seg,) tensor of sum_{p, c} out[s, p, c]^2, the surpluses never
+        leaving the GPU workspace (sgm_surplus_norms)."""
+        torch = torch_cuda()
+        self._check_inputs(x, f)
+        P, NF = x.shape[0], f.shape[1]
+        sumsq = torch.zeros(self.n_seg, dtype=torch.float64, device=x.device)
+        if P == 0 or self.n_seg == 0:
+            return sumsq
+        need = int(_lib.load().sgm_surplus_norms_workspace_bytes(self._h, P, NF))
+        ws = self.workspace(P, NF, need)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().sgm_surplus_norms(
+            self._h, x.data_ptr(), P, x.stride(0) if P > 1 else max(x.shape[1], 1),
+            f.data_ptr(), f.shape[0], NF, f.stride(0) if f.shape[0] > 1 else max(NF, 1),
+            sumsq.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return sumsq
+
+    def reload_knobs(self):
+        _lib.check(_lib.load().sgm_plan_reload_knobs(self._h))
 
     def take_flags(self):
         torch = torch_cuda()

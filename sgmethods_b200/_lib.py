@@ -34,7 +34,8 @@ class PlanDesc(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("N", c_i32), ("T", c_i64), ("M", c_i64),
                 ("coeffs", p_f64), ("term_fam", p_i32), ("map_off", p_i64), ("maps", p_i32),
                 ("n_fam", c_i32), ("fam_off", p_i64), ("fam_knots", p_f64),
-                ("fam_lambda", p_f64), ("fam_newrank", p_i32)]
+                ("fam_lambda", p_f64), ("fam_newrank", p_i32),
+                ("n_seg", c_i32), ("seg_off", p_i64)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sgm_b200.h
@@ -59,6 +60,13 @@ SIGNATURES = {
     "sgm_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.c_int,
                                        ctypes.POINTER(c_vp)]),
     "sgm_plan_destroy": (None, [c_vp]),
+    "sgm_plan_reload_knobs": (ctypes.c_int, [c_vp]),
+    "sgm_eval_segments": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                         c_i64, c_i64, c_vp, c_sz, c_vp]),
+    "sgm_segment_sumsq": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "sgm_surplus_norms_workspace_bytes": (c_sz, [c_vp, c_i64, c_i64]),
+    "sgm_surplus_norms": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                         c_vp, c_sz, c_vp]),
     "sgm_plan_table_bytes": (c_i64, [c_vp]),
     "sgm_plan_corners_per_point": (c_i64, [c_vp]),
     "sgm_plan_take_flags": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_uint32)]),
@@ -115,6 +123,9 @@ def load():
                     raise ImportError(
                         "sgmethods_b200 needs its CUDA library libsgm_b200.so and there is no "
                         "CPU fallback; build it with `make -C sgmethods_b200/csrc`") from exc
+                import warnings
+                warnings.warn("libsgm_b200.so is older than its sources and could not be rebuilt "
+                              f"({exc}); loading the existing library", RuntimeWarning)
         lib = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)

@@ -2,21 +2,28 @@
 (Gerstner-Griebel indicators on the reduced margin).
 
 Same function name and argument list as the reference's
-sgmethods/compute_error_indicators.py (compute_GG_indicators_RM :16-121).  The reference is
-broken as shipped (it reads ``mid_set.reducedMargin`` / ``mid_set.midSet``; MidSet defines
-``reduced_margin`` / ``mid_set``); this module implements the
-documented behaviour: for every multi-index nu of the reduced margin that has no recycled
-value, the indicator is  L2_err_param( I_{Lambda + nu}[u](yy_rnd), u_interp ).
+sgmethods/compute_error_indicators.py (compute_GG_indicators_RM :16-121).  The reference
+raises AttributeError as shipped (it reads ``mid_set.reducedMargin`` / ``mid_set.midSet``;
+MidSet defines ``reduced_margin`` / ``mid_set``); its code runs
+unmodified on a MidSet that carries those names as aliases, and the outputs of such runs are
+this module's parity fixtures (tests/golden/gg_*.npz, tests/golden/make_golden.py): for every
+multi-index nu of the reduced margin that has no recycled value, the indicator is
+L2_err_param( I_{Lambda + nu}[u](yy_rnd), u_interp ).
 
-Two evaluation methods (keyword ``method``):
+Evaluation methods (keyword ``method``):
 
-  * ``"surplus"`` (default): I_{Lambda+nu}[u] - I_Lambda[u] is the hierarchical surplus
-    Delta_nu u = sum_{e in {0,1}^N, e <= supp(nu)} (-1)^{|e|} TP_{nu-e}[u], i.e. only 2^{|supp nu|}
-    tensor-product terms.  Each candidate gets a tiny plan with exactly those terms (built
-    by the O(sum S_t) native table builder), samples on nodes that already belong to the
-    current sparse grid are recycled through the hashed row matcher, only the new nodes of
-    TP_nu call ``f``, and ``u_interp + Delta_nu u`` is formed on the GPU.  Cost per candidate:
-    2^k terms instead of re-evaluating all terms of the extended interpolant.
+  * ``"surplus"`` (default) -- ONE batched launch for all candidates.
+    I_{Lambda+nu}[u] - I_Lambda[u] is the hierarchical surplus
+    Delta_nu u = sum_{e in {0,1}^N, e <= supp(nu)} (-1)^{|e|} TP_{nu-e}[u], i.e. 2^{|supp nu|}
+    tensor-product terms.  The terms of ALL candidates go into one segmented plan (one
+    segment per candidate; tables from the O(sum S_t) native builder, nodes numbered jointly so
+    that a node shared by several candidates is sampled once), samples on nodes of the
+    current sparse grid are recycled through the hashed row matcher, only genuinely new nodes
+    call ``f``, and ``sgm_eval_segments`` evaluates every candidate's surplus at ``yy_rnd`` in
+    one launch (bracket tables built once per point).  ``u_interp + Delta_nu u`` is formed on
+    the GPU and handed to the norm callback -- or, when the callback is a ``MeanSquareNorm``,
+    the norms are reduced on the GPU (``sgm_surplus_norms``) and only one float per candidate
+    crosses PCIe.
   * ``"rebuild"``: the reference's own sequence (extended SGInterpolant, recycled sampling,
     full evaluation) with the fast constructor and the fused kernel.
 
@@ -34,17 +41,31 @@ from .tp_inteprolants import TPPwLinearInterpolator, resolve_kind
 from .utils import find_mid, lexic_sort
 
 
-def _surplus_tables(nu, knots, lev2knots):
-    """Packed tables of Delta_nu = sum_e (-1)^{|e|} TP_{nu-e}: (coeffs, num_nodes, fam_m,
-    fam_off, fam_knots, term_fam, grid)."""
-    supp = np.flatnonzero(nu > 0)
-    rows, coeffs = [], []
-    for bits in product((0, 1), repeat=supp.size):
-        e = np.zeros_like(nu)
-        e[supp] = bits
-        rows.append(lev2knots(nu - e).astype(int))
-        coeffs.append(-1.0 if sum(bits) % 2 else 1.0)
-    num_nodes = np.asarray(rows, dtype=np.int32).reshape(len(rows), nu.size)
+class MeanSquareNorm:
+    """The Monte-Carlo L2 norm  sqrt( mean_p sum_c (a[p, c] - b[p, c])^2 )  as a callable.
+    Passing an instance as ``L2_err_param`` lets ``compute_GG_indicators_RM`` reduce the norm
+    of every candidate on the GPU instead of calling back into Python per candidate."""
+
+    def __call__(self, a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        d = (a - b).reshape(a.shape[0], -1)
+        return float(np.sqrt(np.mean(np.sum(d * d, axis=1))))
+
+
+def _surplus_tables(candidates, knots, lev2knots):
+    """Packed tables of Delta_nu = sum_e (-1)^{|e|} TP_{nu-e} for every candidate nu, one
+    segment per candidate: (coeffs, term_fam, fam_off, fam_knots, seg_off, grid)."""
+    rows, coeffs, seg_off = [], [], [0]
+    for nu in candidates:
+        supp = np.flatnonzero(nu > 0)
+        for bits in product((0, 1), repeat=supp.size):
+            e = np.zeros_like(nu)
+            e[supp] = bits
+            rows.append(lev2knots(nu - e).astype(int))
+            coeffs.append(-1.0 if sum(bits) % 2 else 1.0)
+        seg_off.append(len(rows))
+    N = candidates[0].size
+    num_nodes = np.asarray(rows, dtype=np.int32).reshape(len(rows), N)
     fam_m = np.unique(num_nodes[num_nodes > 1]).astype(np.int32)
     fam_list = [np.atleast_1d(np.asarray(knots(np.int64(m)), dtype=np.float64)) for m in fam_m]
     fam_off = np.concatenate(([0], np.cumsum(fam_m, dtype=np.int64))).astype(np.int64)
@@ -53,7 +74,13 @@ def _surplus_tables(nu, knots, lev2knots):
     lut[fam_m] = np.arange(fam_m.size, dtype=np.int32)
     term_fam = np.where(num_nodes > 1, lut[np.minimum(num_nodes, lut.size - 1)], -1)
     grid = _lib.HostGrid(num_nodes, fam_m, fam_off, fam_knots, NODE_TOL)
-    return np.asarray(coeffs), term_fam.astype(np.int32), fam_off, fam_knots, grid
+    return (np.asarray(coeffs), term_fam.astype(np.int32), fam_off, fam_knots,
+            np.asarray(seg_off, dtype=np.int64), grid, fam_m)
+
+
+# candidates per batched launch are bounded so that the (n_cand, P, NF) surplus buffer stays
+# below this many bytes
+_BATCH_BYTES = 1 << 30
 
 
 def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
@@ -112,30 +139,54 @@ def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
 
     kind = resolve_kind(TP_inteporlant)
     u_on_SG = np.atleast_2d(np.asarray(u_on_SG, dtype=np.float64))
+    NF = u_on_SG.shape[1]
+    P = yy_dev.shape[0]
     SG_cur = np.asarray(SG, dtype=np.float64)
     if SG_cur.shape[1] < N:          # the current grid lives in fewer dimensions: embed it
         SG_cur = np.hstack((SG_cur, np.zeros((SG_cur.shape[0], N - SG_cur.shape[1]))))
     u_cur = np.asarray(u_interp, dtype=np.float64)
-    u_cur_dev = torch.from_numpy(np.ascontiguousarray(u_cur.reshape(yy_dev.shape[0], -1))).to(device)
-    for i in to_compute:
-        nu = np.asarray(reduced_margin[i, :])
-        coeffs, term_fam, fam_off, fam_knots, grid = _surplus_tables(nu, knots, lev2knots)
+    u_cur_dev = torch.from_numpy(np.ascontiguousarray(u_cur.reshape(P, -1))).to(device)
+    on_gpu = isinstance(L2_err_param, MeanSquareNorm)
+    per_batch = max(1, int(_BATCH_BYTES // max(1, P * NF * 8)))
+    for lo in range(0, len(to_compute), per_batch):
+        batch = to_compute[lo:lo + per_batch]
+        cands = [np.asarray(reduced_margin[i, :]) for i in batch]
+        coeffs, term_fam, fam_off, fam_knots, seg_off, grid, fam_m = \
+            _surplus_tables(cands, knots, lev2knots)
+        if kind == _lib.KIND_CUBIC and fam_m.size and fam_m.min() < 4:
+            raise UnboundLocalError("pw-cubic interpolation needs at least 4 knots in every "
+                                    "active direction")      # as the reference (:232)
         map_off, maps = grid.maps()
         nodes = grid.nodes_dense()
-        # values on the nodes of the 2^k surplus terms: recycle what the current grid has
+        # values on the nodes of all surplus terms: recycle what the current grid has, sample
+        # the rest (a node new to several candidates is sampled once)
         match = _lib.match_rows(nodes, SG_cur, NODE_TOL)
-        vals = np.zeros((nodes.shape[0], u_on_SG.shape[1]))
+        vals = np.zeros((nodes.shape[0], NF))
         have = match >= 0
         vals[have] = u_on_SG[match[have]]
-        for r in np.flatnonzero(~have):
-            vals[r, :] = f(nodes[r, :])
+        missing = np.flatnonzero(~have)
+        if missing.size:
+            if n_parallel > 1:
+                from multiprocessing import Pool
+                with Pool(n_parallel) as pool:
+                    got = np.array(pool.map(f, [nodes[r, :] for r in missing]))
+                vals[missing] = got.reshape(missing.size, -1)
+            else:
+                for r in missing:
+                    vals[r, :] = f(nodes[r, :])
         plan = DevicePlan(kind, N, nodes.shape[0], coeffs, term_fam, map_off, maps, fam_off,
-                          fam_knots, device=device.index)
-        surplus = plan.eval(yy_dev, torch.from_numpy(vals).to(device))
+                          fam_knots, device=device.index, seg_off=seg_off)
+        vals_dev = torch.from_numpy(vals).to(device)
+        if on_gpu:
+            sumsq = plan.surplus_sumsq(yy_dev, vals_dev)
+            indicators[batch] = np.sqrt(sumsq.cpu().numpy() / P)
+        else:
+            deltas = plan.eval_segments(yy_dev, vals_dev)            # (n_cand, P, NF)
+            u_ext = (u_cur_dev.unsqueeze(0) + deltas).cpu().numpy()  # one D2H for the batch
+            for j, i in enumerate(batch):
+                indicators[i] = L2_err_param(u_ext[j].reshape(u_cur.shape), u_interp)
         if kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot")
-        u_ext = (u_cur_dev + surplus).cpu().numpy().reshape(u_cur.shape)
-        indicators[i] = L2_err_param(u_ext, u_interp)
         plan.close()
         grid.close()
     return indicators

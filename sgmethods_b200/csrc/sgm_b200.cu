@@ -44,14 +44,46 @@ using sgm::TermDim;
 using sgm::TermHdr;
 using sgm::TermRec;
 
+// Development switches, read ONCE when a plan is created -- never on the
+// launch path.  All default to "off" = the measured-best choice; none changes results.
+struct Knobs {
+    int force_kernel = 0;        // SGM_FORCE_KERNEL: 1 = v1, 2 = split, 3 = prefix
+    int prefix_run = 8;          // SGM_PREFIX_RUN
+    bool prefix_unbalanced = false;
+    int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
+    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false;
+    int wide_pairs = -1;         // SGM_WIDE_PAIRS: -1 = automatic, 0 | 1
+    long long col_loop_max = -1; // SGM_COL_LOOP_MAX
+    static Knobs from_env() {
+        Knobs k;
+        if (const char* v = std::getenv("SGM_FORCE_KERNEL"))
+            k.force_kernel = !std::strcmp(v, "v1") ? 1 : !std::strcmp(v, "split") ? 2 : !std::strcmp(v, "prefix") ? 3 : 0;
+        if (const char* v = std::getenv("SGM_PREFIX_RUN")) k.prefix_run = std::atoi(v);
+        k.prefix_unbalanced = std::getenv("SGM_PREFIX_UNBALANCED") != nullptr;
+        if (const char* v = std::getenv("SGM_PREFIX_PPL")) k.prefix_ppl = std::atoi(v);
+        k.no_sort = std::getenv("SGM_NO_SORT") != nullptr;
+        k.no_wide = std::getenv("SGM_NO_WIDE") != nullptr;
+        k.no_idx8 = std::getenv("SGM_NO_IDX8") != nullptr;
+        k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
+        k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
+        if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
+        if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
+        return k;
+    }
+};
+
 struct sgm_plan {
     int device = 0;
     PlanDev dev{};
+    Knobs knobs{};
+    int64_t M = 0;               // rows of f the node maps were validated against
+    int n_seg = 0;               // > 0: segmented plan (sgm_eval_segments only)
     int64_t n_vals = 0;          // sum_t S_t
     int64_t corners = 0;         // sum_t C_t
     bool all_packed = false;     // every term has a packed record (needed by the H1 kernel)
     bool prefix_ok = false;      // tables of the prefix kernel (pw-linear, all packed) are built
-    int prefix_wins = -1;        // cached occupancy comparison prefix vs split kernel (-1: not yet)
+    int prefix_wins = 0;         // occupancy comparison prefix vs split kernel (plan creation)
+    bool prefix_launch_ok = false;
     int64_t table_bytes = 0;
     int kmax = 0;
     int max_entry_n = 0;         // largest knot family among the table entries
@@ -61,6 +93,19 @@ struct sgm_plan {
 };
 
 namespace {
+
+// Entry points run on the plan's device and leave the caller's current device untouched.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device)
+            switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 template <class T>
 int upload(sgm_plan* plan, const std::vector<T>& host, const T** dev_ptr) {
@@ -165,7 +210,7 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
     // SM wins (independent blocks overlap each other's chunk barriers)
     const int cand[6][3] = {{16, 64, 0}, {8, 32, 0}, {8, 64, 0}, {4, 32, 0}, {32, 128, 0}, {16, 48, 1}};
     const bool idx8_ok = KIND == SGM_PW_LINEAR && plan->all_packed && plan->max_entry_n <= 257 &&
-                         !std::getenv("SGM_NO_IDX8");            // (dev knob)
+                         !plan->knobs.no_idx8;
     for (const auto& c : cand) {
         if (c[0] == 32 && KIND != SGM_PW_LINEAR) continue;
         if (c[2] && !idx8_ok) continue;
@@ -192,8 +237,7 @@ int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsig
                   size_t scratch_bytes, cudaStream_t stream, const int** perm,
                   int64_t min_points = kSortMinPoints) {
     *perm = nullptr;
-    const char* nosort = std::getenv("SGM_NO_SORT");          // dev knob
-    if (!(P >= min_points && P < 0x7fffffff && plan->dev.n_key >= 4 && !nosort)) return SGM_OK;
+    if (!(P >= min_points && P < 0x7fffffff && plan->dev.n_key >= 4 && !plan->knobs.no_sort)) return SGM_OK;
     const size_t need = sort_scratch_bytes(P);
     if (scratch_bytes < need) return sgm_fail(SGM_ERR_WORKSPACE, "workspace too small for the point sort");
     int* perm_w = reinterpret_cast<int*>(scratch);
@@ -222,10 +266,9 @@ PrefixLaunch choose_prefix_launch(const sgm_plan* plan, int ppl = 1) {
     const PlanDev& d = plan->dev;
     PrefixLaunch none{0, 0, 0, 0, nullptr, 1};
     if (!plan->prefix_ok) return none;
-    const char* env = std::getenv("SGM_PREFIX_RUN");           // dev knob: mean terms per warp run
-    const int want = env ? std::atoi(env) : 8;
+    const int want = plan->knobs.prefix_run;                   // mean terms per warp run
     const int warps = 8;
-    const bool balanced = !std::getenv("SGM_PREFIX_UNBALANCED");   // dev knob
+    const bool balanced = !plan->knobs.prefix_unbalanced;
     const int cand[2] = {want, 4};
     for (int run : cand) {
         SplitKernel kern = nullptr;
@@ -252,20 +295,25 @@ PrefixLaunch choose_prefix_launch(const sgm_plan* plan, int ppl = 1) {
 
 // true when the scalar evaluation of this plan / batch goes through the prefix kernel (the
 // value tables are then gathered in its first-direction-fastest layout)
-bool use_prefix_kernel(sgm_plan* plan, int64_t P) {
+bool use_prefix_kernel(const sgm_plan* plan, int64_t P) {
     if (!plan->prefix_ok || plan->dev.kind != SGM_PW_LINEAR) return false;
-    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split" | "prefix"
-    if (force) return std::strcmp(force, "prefix") == 0 && choose_prefix_launch(plan).warps > 0;
+    if (plan->knobs.force_kernel) return plan->knobs.force_kernel == 3 && plan->prefix_launch_ok;
     if (plan->dev.T < 32 && P >= 16384) return false;         // few terms, many points: kernel A
-    // large bracket tables (many directions x levels) limit the resident blocks: the split
-    // kernel's 16-warp blocks then keep more warps on the SM, which matters more than the
-    // prefix reuse (config 5, d=128: 8 vs 16 resident warps, 110 vs 85 ms per 10^5 points)
-    if (plan->prefix_wins < 0) {                              // decided once per plan
-        const PrefixLaunch L = choose_prefix_launch(plan);
-        const SplitLaunch S = choose_split_launch<SGM_PW_LINEAR>(plan);
-        plan->prefix_wins = L.warps > 0 && 4 * L.warps * L.blocks_per_sm >= 3 * S.warps * S.blocks_per_sm;
-    }
-    return plan->prefix_wins > 0;
+    return plan->prefix_wins > 0;                             // decided at plan creation
+}
+
+// Large bracket tables (many directions x levels) limit the resident blocks: the split
+// kernel's 16-warp blocks then keep more warps on the SM, which matters more than the prefix
+// reuse (config 5, d=128: 8 vs 16 resident warps, 110 vs 85 ms per 10^5 points).  Called once,
+// at the end of plan creation (the plan is read-only afterwards).
+void decide_prefix(sgm_plan* plan) {
+    plan->prefix_wins = 0;
+    plan->prefix_launch_ok = false;
+    if (!plan->prefix_ok || plan->dev.kind != SGM_PW_LINEAR) return;
+    const PrefixLaunch L = choose_prefix_launch(plan);
+    const SplitLaunch S = choose_split_launch<SGM_PW_LINEAR>(plan);
+    plan->prefix_launch_ok = L.warps > 0;
+    plan->prefix_wins = L.warps > 0 && 4 * L.warps * L.blocks_per_sm >= 3 * S.warps * S.blocks_per_sm;
 }
 
 int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
@@ -275,10 +323,10 @@ int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx
     if (L.warps == 0) return sgm_fail(SGM_ERR_INVALID, "prefix kernel not available for this plan");
     {   // two points per lane once the batch fills every SM with such tiles (config 2: 27.7 ->
         // 25.0 ms); smaller batches keep 32-point tiles for the parallelism
-        const char* env_ppl = std::getenv("SGM_PREFIX_PPL");   // dev knob: force 1 | 2
+        const int force_ppl = plan->knobs.prefix_ppl;
         const PrefixLaunch L2 = choose_prefix_launch(plan, 2);
         const bool fills = P >= (int64_t)64 * plan->sm_count * std::max(L2.blocks_per_sm, 1);
-        if (L2.warps > 0 && (env_ppl ? std::atoi(env_ppl) == 2 : fills)) L = L2;
+        if (L2.warps > 0 && (force_ppl ? force_ppl == 2 : fills)) L = L2;
     }
     const int64_t tiles = (P + 32 * L.ppl - 1) / (32 * L.ppl);
     const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
@@ -301,9 +349,8 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                         double* out, int64_t ldo, double scale, int accumulate,
                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const SplitLaunch L = choose_split_launch<KIND>(plan);
-    const char* force = std::getenv("SGM_FORCE_KERNEL");      // dev knob: "v1" | "split" | "prefix"
-    const bool want_v1 = force ? std::strcmp(force, "v1") == 0
-                               : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
+    const bool want_v1 = plan->knobs.force_kernel ? plan->knobs.force_kernel == 1
+                                                  : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
     if (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8)   // few terms / huge tables
         return launch_points<KIND>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch,
                                    scratch_bytes, stream);
@@ -314,7 +361,7 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
         int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
         if (rc) return rc;
     }
-    if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !std::getenv("SGM_NO_H1")) {
+    if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !plan->knobs.no_h1) {
         constexpr int HW = 16;
         const PlanDev& d = plan->dev;
         const size_t smem = (size_t)d.n_knots * 16 + (size_t)d.B * 32 * 8 + (size_t)HW * 32 * 8 +
@@ -453,13 +500,11 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
     // the guarded kernel; needs 16-byte aligned rows
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                          (ldf % 2 == 0) && (ldo % 2 == 0);
-    const char* nowide = std::getenv("SGM_NO_WIDE");          // dev knob
-    if (aligned && !nowide && NF >= 64 && plan->dev.n_corners > 0) {
+    if (aligned && !plan->knobs.no_wide && NF >= 64 && plan->dev.n_corners > 0) {
         const int tile = NF >= 512 ? 256 : (NF >= 128 ? 128 : 64);
         const int64_t n_tiles = NF / tile;
-        const char* pairs = std::getenv("SGM_WIDE_PAIRS");     // dev knob: 0 | 1
         bool launched = false;
-        if (perm && !(pairs && pairs[0] == '0')) {
+        if (perm && plan->knobs.wide_pairs != 0) {
             // the pair kernel guards its last tile: all (even many) columns in one launch,
             // an odd last column through the guarded narrow kernel
             const int64_t even = NF & ~(int64_t)1;
@@ -506,10 +551,12 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     if (!plan) return sgm_fail(SGM_ERR_INVALID, "eval: null plan");
     if (P < 0 || NF < 1 || ldx < plan->dev.N || ldf < NF || ldo < NF)
         return sgm_fail(SGM_ERR_INVALID, "eval: bad shapes / leading dimensions");
-    if (M != 0 && M < 0) return sgm_fail(SGM_ERR_INVALID, "eval: bad M");
+    if (M < plan->M)
+        return sgm_failf(SGM_ERR_INVALID, "eval: f has %lld rows, the plan's node maps address %lld",
+                         (long long)M, (long long)plan->M);
     if (P == 0) return SGM_OK;
     if (!x || !f || !out) return sgm_fail(SGM_ERR_INVALID, "eval: null buffer");
-    SGM_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard guard(plan->device);
     const int kind = plan->dev.kind;
     // one scalar evaluation (kernel A family) of column `col` of f into column `col` of out
     auto scalar_column = [&](int64_t col) -> int {
@@ -562,11 +609,10 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     // column goes through the scalar kernel (one launch per column, the tables stay in L2).
     // Wide outputs: full 128/256-column tiles through the column kernels, the ragged rest
     // column by column.
-    const char* env = std::getenv("SGM_COL_LOOP_MAX");          // dev knob
     // measured (tools/exp_nf*.py): the packed pw-linear scalar kernel beats every column
     // kernel below 128 columns; for the nested-walk kinds the crossover is 16..25 columns
     const bool fast_scalar = (kind == SGM_PW_LINEAR && plan->kmax <= 4) || kind == SGM_HIER_PW_LINEAR;
-    const int64_t col_loop_max = env ? std::atoll(env) : (fast_scalar ? 127 : 16);
+    const int64_t col_loop_max = plan->knobs.col_loop_max >= 0 ? plan->knobs.col_loop_max : (fast_scalar ? 127 : 16);
     const int64_t wide_cols = NF >= 512 ? NF / 256 * 256
                               : (NF >= 128 ? NF / 128 * 128 : (fast_scalar ? 0 : NF / 64 * 64));
     const bool aligned = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
@@ -576,11 +622,10 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         // all columns (its last 256-column tile is guarded), instead of full tiles + a ragged
         // remainder through the narrower kernels (config 4, NF = 1000: 84 -> 67 ms).  A short
         // tail of a packed pw-linear plan still goes column by column through the scalar kernel.
-        const char* pairs = std::getenv("SGM_WIDE_PAIRS");     // dev knob: 0 | 1
         const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
         const bool pairs_ok = aligned && plan->dev.n_corners > 0 && NF >= 512 && P >= kSortMinPointsCols &&
-                              P < 0x7fffffff && plan->dev.n_key >= 4 && !std::getenv("SGM_NO_SORT") &&
-                              !(pairs && pairs[0] == '0') && workspace &&
+                              P < 0x7fffffff && plan->dev.n_key >= 4 && !plan->knobs.no_sort &&
+                              plan->knobs.wide_pairs != 0 && workspace &&
                               workspace_bytes > g_bytes + sort_scratch_bytes(P);
         if (pairs_ok) {
             const int64_t tail = NF % 256;
@@ -607,6 +652,106 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     return SGM_OK;
 }
 
+// Segmented evaluation: out[s, p, :] = sum over the terms of segment s.  Scalar outputs (and
+// few columns, one at a time) through the split kernel's SEG flavour on pre-gathered values,
+// wider outputs through the guarded lanes-across-columns kernel.
+template <int KIND>
+SplitKernel split_seg_kernel_for(int warps, int chunk) {
+    if (warps == 16 && chunk == 64) return sgm::eval_points_split_kernel<KIND, 16, 64, false, true>;
+    if (warps == 8 && chunk == 32) return sgm::eval_points_split_kernel<KIND, 8, 32, false, true>;
+    return sgm::eval_points_split_kernel<KIND, 4, 32, false, true>;
+}
+
+template <int KIND>
+int launch_segments_scalar(sgm_plan* plan, const PlanDev& dev, const double* x, int64_t P, int64_t ldx,
+                           const double* G, double* out, int64_t ldo, cudaStream_t stream) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1) + (size_t)d.B * 32 * 8 +
+                         32 * 8 + 64 + (size_t)d.E * 32 * 2;
+    const int cand[3][2] = {{16, 64}, {8, 32}, {4, 32}};
+    for (const auto& c : cand) {
+        const size_t smem = fixed + 2 * (size_t)c[1] * 32 * 8;
+        if (smem > (size_t)plan->max_smem_optin) continue;
+        SplitKernel kern = split_seg_kernel_for<KIND>(c[0], c[1]);
+        SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int bps = 0;
+        SGM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, c[0] * 32, smem));
+        if (bps < 1) continue;
+        const int64_t tiles = (P + 31) / 32;
+        const int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * bps);
+        kern<<<(unsigned)blocks, c[0] * 32, smem, stream>>>(dev, x, P, ldx, G, out, ldo, 1.0, 0, nullptr);
+        SGM_CUDA(cudaGetLastError());
+        return SGM_OK;
+    }
+    return sgm_fail(SGM_ERR_OVERFLOW, "eval_segments: bracket tables exceed shared memory");
+}
+
+template <int KIND, int CPL>
+int launch_segments_cols(sgm_plan* plan, const PlanDev& dev, const double* x, int64_t P, int64_t ldx,
+                         const double* f, int64_t ldf, int64_t NF, double* out, int64_t ldo,
+                         cudaStream_t stream) {
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE ? 2 : 1);
+    const size_t per_warp = (size_t)d.B * 8 + (size_t)d.E * 4;
+    int warps = 8;
+    while (warps > 1 && fixed + per_warp * warps > (size_t)plan->max_smem_optin) warps >>= 1;
+    const size_t smem = fixed + per_warp * warps;
+    if (smem > (size_t)plan->max_smem_optin)
+        return sgm_fail(SGM_ERR_OVERFLOW, "eval_segments: per-point basis table exceeds shared memory");
+    const int pts_per_block = warps * 8;
+    const int64_t gx = (P + pts_per_block - 1) / pts_per_block;
+    const int64_t gy = (NF + 32 * CPL - 1) / (32 * CPL);
+    if (gx > 0x7fffffff || gy > 65535) return sgm_fail(SGM_ERR_OVERFLOW, "grid too large");
+    auto kern = sgm::eval_cols_kernel<KIND, CPL, true>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)gy), warps * 32, smem, stream>>>(
+        dev, x, P, ldx, f, ldf, NF, out, ldo, 1.0, 0, pts_per_block);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+template <int KIND>
+int eval_segments_kind(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                       int64_t NF, int64_t ldf, double* out, int64_t ldo, int64_t seg_stride,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    PlanDev dev = plan->dev;                   // per-launch copy carrying the output stride
+    dev.seg_stride = seg_stride;
+    if (NF >= 24) {
+        constexpr int CK = sgm::base_kind(KIND);
+        if (NF <= 32) return launch_segments_cols<CK, 1>(plan, dev, x, P, ldx, f, ldf, NF, out, ldo, stream);
+        if (NF <= 64) return launch_segments_cols<CK, 2>(plan, dev, x, P, ldx, f, ldf, NF, out, ldo, stream);
+        return launch_segments_cols<CK, 4>(plan, dev, x, P, ldx, f, ldf, NF, out, ldo, stream);
+    }
+    const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+    if (workspace_bytes < g_bytes || !workspace)
+        return sgm_fail(SGM_ERR_WORKSPACE, "eval_segments: workspace too small");
+    double* G = static_cast<double*>(workspace);
+    const int64_t n = plan->n_vals;
+    const int gblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plan->sm_count * 8);
+    for (int64_t col = 0; col < NF; ++col) {
+        sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(plan->dev.maps, n, f + col, ldf, 1, G);
+        SGM_CUDA(cudaGetLastError());
+        int rc = launch_segments_scalar<KIND>(plan, dev, x, P, ldx, G, out + col, ldo, stream);
+        if (rc) return rc;
+    }
+    return SGM_OK;
+}
+
+int eval_segments(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t NF,
+                  int64_t ldf, double* out, int64_t ldo, int64_t seg_stride, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
+    switch (plan->dev.kind) {
+        case SGM_PW_LINEAR:
+            if (plan->kmax > 4)
+                return eval_segments_kind<sgm::SGM_LINEAR_WIDE>(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes, stream);
+            return eval_segments_kind<SGM_PW_LINEAR>(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes, stream);
+        case SGM_PW_QUADRATIC: return eval_segments_kind<SGM_PW_QUADRATIC>(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes, stream);
+        case SGM_PW_CUBIC: return eval_segments_kind<SGM_PW_CUBIC>(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes, stream);
+        case SGM_LAGRANGE: return eval_segments_kind<SGM_LAGRANGE>(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes, stream);
+        default: return sgm_fail(SGM_ERR_INVALID, "eval_segments: unsupported plan kind");
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -625,6 +770,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     if (desc->T > 0 && (!desc->coeffs || !desc->term_fam || !desc->map_off || !desc->maps))
         return sgm_fail(SGM_ERR_INVALID, "plan_create: null table");
     if (desc->T > 0x7fffffff) return sgm_fail(SGM_ERR_OVERFLOW, "plan_create: too many terms");
+    if (desc->n_seg < 0 || (desc->n_seg > 0 && desc->kind == SGM_HIER_PW_LINEAR))
+        return sgm_fail(SGM_ERR_INVALID, "plan_create: bad segment count / segmented hierarchical plan");
     const int kind = desc->kind;
     const int N = desc->N;
     const int64_t T = desc->T;
@@ -722,14 +869,16 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         r.info = h.k & 0xff;
         bool packable = (kind == SGM_PW_LINEAR || kind == SGM_HIER_PW_LINEAR) && h.k <= 4 &&
                         (h.k == 0 || kind == SGM_HIER_PW_LINEAR || tdim[h.dim_off + h.k - 1].stride == 1);
-        if (packable) ++n_packed;
         for (int j = 0; j < h.k && packable; ++j) {
             const TermDim& d = tdim[h.dim_off + j];
             if (d.ent > 0xffff || d.stride > 0xffff) { packable = false; break; }
             r.ent[j] = (unsigned short)d.ent;
             r.stride[j] = (unsigned short)d.stride;
         }
-        if (packable) r.info |= sgm::TERMREC_PACKED;
+        if (packable) {                   // counted only when the record really is packed
+            r.info |= sgm::TERMREC_PACKED;
+            ++n_packed;
+        }
         corners += ncorner;
         kmax = std::max(kmax, h.k);
     }
@@ -859,9 +1008,11 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     int dev_count = 0;
     SGM_CUDA(cudaGetDeviceCount(&dev_count));
     if (device < 0 || device >= dev_count) return sgm_fail(SGM_ERR_INVALID, "plan_create: bad device");
-    SGM_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     sgm_plan* plan = new sgm_plan();
     plan->device = device;
+    plan->knobs = Knobs::from_env();
+    plan->M = desc->M;
     cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     plan->n_vals = desc->map_off[T];
@@ -941,16 +1092,46 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         return rc;
     }
     d.flags = const_cast<unsigned*>(cflags);
+    d.seg_id = nullptr;
+    d.seg_stride = 0;
+    if (desc->n_seg > 0) {
+        if (!desc->seg_off || desc->seg_off[0] != 0 || desc->seg_off[desc->n_seg] != T) {
+            sgm_plan_destroy(plan);
+            return sgm_fail(SGM_ERR_INVALID, "plan_create: segment offsets must run from 0 to T");
+        }
+        std::vector<int> seg_id((size_t)T);
+        for (int sgi = 0; sgi < desc->n_seg; ++sgi) {
+            if (desc->seg_off[sgi + 1] <= desc->seg_off[sgi]) {
+                sgm_plan_destroy(plan);
+                return sgm_fail(SGM_ERR_INVALID, "plan_create: empty or unordered segment");
+            }
+            for (int64_t t = desc->seg_off[sgi]; t < desc->seg_off[sgi + 1]; ++t) seg_id[t] = sgi;
+        }
+        if ((rc = upload(plan, seg_id, &d.seg_id))) {
+            sgm_plan_destroy(plan);
+            return rc;
+        }
+        plan->n_seg = desc->n_seg;
+    }
     plan->prefix_ok = !prec.empty();
     if (!plan->prefix_ok) { d.prec = nullptr; d.gmaps = nullptr; d.run_start = nullptr; }
     for (int i = 0; i < 6; ++i) d.hgroup[i] = hgroup[i];
+    decide_prefix(plan);
     *out = plan;
+    return SGM_OK;
+}
+
+int sgm_plan_reload_knobs(sgm_plan* plan) {
+    if (!plan) return sgm_fail(SGM_ERR_INVALID, "reload_knobs: null plan");
+    DeviceGuard guard(plan->device);
+    plan->knobs = Knobs::from_env();
+    decide_prefix(plan);
     return SGM_OK;
 }
 
 void sgm_plan_destroy(sgm_plan* plan) {
     if (!plan) return;
-    cudaSetDevice(plan->device);
+    DeviceGuard guard(plan->device);
     for (void* p : plan->allocations) cudaFree(p);
     delete plan;
 }
@@ -960,7 +1141,7 @@ int64_t sgm_plan_corners_per_point(const sgm_plan* plan) { return plan ? plan->c
 
 int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags) {
     if (!plan || !flags) return sgm_fail(SGM_ERR_INVALID, "take_flags: null argument");
-    SGM_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard guard(plan->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned host = 0;
     SGM_CUDA(cudaMemcpyAsync(&host, plan->dev.flags, sizeof host, cudaMemcpyDeviceToHost, s));
@@ -988,8 +1169,58 @@ size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
 int sgm_eval(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f, int64_t M,
              int64_t NF, int64_t ldf, double* out, int64_t ldo, void* workspace,
              size_t workspace_bytes, void* stream) {
+    if (plan && plan->n_seg > 0)
+        return sgm_fail(SGM_ERR_INVALID, "eval: segmented plan (use sgm_eval_segments)");
     return eval_one(plan, x, P, ldx, f, M, NF, ldf, out, ldo, 1.0, 0, workspace, workspace_bytes,
                     static_cast<cudaStream_t>(stream));
+}
+
+int sgm_eval_segments(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                      int64_t M, int64_t NF, int64_t ldf, double* out, int64_t ldo,
+                      int64_t seg_stride, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan || plan->n_seg < 1) return sgm_fail(SGM_ERR_INVALID, "eval_segments: plan has no segments");
+    if (P < 0 || NF < 1 || ldx < plan->dev.N || ldf < NF || ldo < NF || seg_stride < (P > 0 ? (P - 1) * ldo + NF : 0))
+        return sgm_fail(SGM_ERR_INVALID, "eval_segments: bad shapes / leading dimensions");
+    if (M < plan->M) return sgm_fail(SGM_ERR_INVALID, "eval_segments: f has fewer rows than the plan addresses");
+    if (P == 0) return SGM_OK;
+    if (!x || !f || !out) return sgm_fail(SGM_ERR_INVALID, "eval_segments: null buffer");
+    DeviceGuard guard(plan->device);
+    return eval_segments(plan, x, P, ldx, f, NF, ldf, out, ldo, seg_stride, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int sgm_segment_sumsq(const double* vals, int32_t n_seg, int64_t P, int64_t NF, int64_t ld,
+                      int64_t seg_stride, double* sumsq, void* stream) {
+    if (n_seg < 0 || P < 0 || NF < 1 || ld < NF) return sgm_fail(SGM_ERR_INVALID, "segment_sumsq: bad shapes");
+    if (n_seg == 0) return SGM_OK;
+    if (!vals || !sumsq) return sgm_fail(SGM_ERR_INVALID, "segment_sumsq: null buffer");
+    sgm::segment_sumsq_kernel<<<(unsigned)n_seg, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        vals, P, NF, ld, seg_stride, sumsq);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+int sgm_surplus_norms(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                      int64_t M, int64_t NF, int64_t ldf, double* sumsq, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!plan || plan->n_seg < 1) return sgm_fail(SGM_ERR_INVALID, "surplus_norms: plan has no segments");
+    if (P < 0 || NF < 1) return sgm_fail(SGM_ERR_INVALID, "surplus_norms: bad shapes");
+    const size_t eval_ws = sgm_eval_workspace_bytes(plan, P, NF);
+    const size_t slab = align_up((size_t)P * (size_t)NF * 8, 256);
+    if (!workspace || workspace_bytes < eval_ws + slab * (size_t)plan->n_seg)
+        return sgm_fail(SGM_ERR_WORKSPACE, "surplus_norms: workspace too small (sgm_surplus_norms_workspace_bytes)");
+    double* deltas = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + align_up(eval_ws, 256));
+    int rc = sgm_eval_segments(plan, x, P, ldx, f, M, NF, ldf, deltas, NF, (int64_t)(slab / 8), workspace,
+                               eval_ws, stream);
+    if (rc) return rc;
+    DeviceGuard guard(plan->device);
+    return sgm_segment_sumsq(deltas, plan->n_seg, P, NF, NF, (int64_t)(slab / 8), sumsq, stream);
+}
+
+size_t sgm_surplus_norms_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
+    if (!plan) return 256;
+    return align_up(sgm_eval_workspace_bytes(plan, P, NF), 256) +
+           align_up((size_t)P * (size_t)NF * 8, 256) * (size_t)std::max(plan->n_seg, 1) + 256;
 }
 
 int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_parts,

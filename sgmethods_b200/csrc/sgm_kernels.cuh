@@ -73,6 +73,10 @@ struct PlanDev {
     const TermRec* hrec;               // SGM_HIER_PW_LINEAR: records grouped by number of directions
     int hgroup[6];                     // hrec[hgroup[k] .. hgroup[k+1]) = terms with k directions
     unsigned* flags;
+    // segmented plans (sgm_eval_segments): segment of every term (consecutive, ascending) and
+    // the distance in doubles between the outputs of consecutive segments; null otherwise
+    const int* seg_id;
+    int64_t seg_stride;
     // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
     // coarsest knot family used in that direction), for the n_key most used directions
     int n_key;
@@ -421,7 +425,11 @@ __host__ __device__ constexpr int split_min_blocks(int kind) {
 // IDX8 (pw-linear plans whose terms are all packed and whose knot families have <= 257 knots):
 // bracket indices are stored as bytes, which brings the tables of config 5 (288 entries) under
 // the size that lets TWO 16-warp blocks share an SM instead of one 32-warp block.
-template <int KIND, int W, int CHUNK, bool IDX8 = false>
+// SEG (segmented plans, sgm_eval_segments): the warp that adds up the products writes the
+// running sum to the output slab of the term's segment whenever a segment ends, and restarts
+// from 0 -- one launch evaluates many small independent interpolants (the hierarchical
+// surpluses of all refinement candidates) on shared bracket tables.
+template <int KIND, int W, int CHUNK, bool IDX8 = false, bool SEG = false>
 __global__ void __launch_bounds__(W * 32, split_min_blocks(KIND))
 eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                          const double* __restrict__ G, double* __restrict__ out, int64_t ldo,
@@ -505,7 +513,24 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
                 sp[tl * 32] = coef * tp;
             }
             __syncthreads();
-            if (warp == (int)(gc & (unsigned)(W - 1))) {
+            if (SEG) {
+                if (warp == (int)(gc & (unsigned)(W - 1))) {
+                    double o = (t0 == 0) ? 0.0 : sOut[lane];
+                    for (int tl = 0; tl < nt; ++tl) {
+                        o = o + sp[tl * 32];
+                        const int t = t0 + tl;
+                        const int sg = __ldg(pl.seg_id + t);
+                        if (t + 1 == pl.T || __ldg(pl.seg_id + t + 1) != sg) {      // warp-uniform
+                            if (valid) {
+                                double* dst = out + (int64_t)sg * pl.seg_stride + p * ldo;
+                                *dst = accumulate ? *dst + scale * o : scale * o;
+                            }
+                            o = 0.0;
+                        }
+                    }
+                    sOut[lane] = o;
+                }
+            } else if (warp == (int)(gc & (unsigned)(W - 1))) {
                 double o = (t0 == 0) ? 0.0 : sOut[lane];
                 for (int tl = 0; tl < nt; ++tl) o = o + sp[tl * 32];
                 if (t0 + chunk >= pl.T) {
@@ -952,7 +977,7 @@ __global__ void pregather_kernel(const int* __restrict__ maps, int64_t n_vals,
 // The 32 lanes first compute the weights and rows of 32 corners in parallel, then the
 // warp walks them in reference order, sharing weight and row by shuffles.
 // ---------------------------------------------------------------------------------------
-template <int KIND, int CPL>
+template <int KIND, int CPL, bool SEG = false>
 __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
                                  int64_t ldx, const double* __restrict__ f, int64_t ldf,
                                  int64_t NF, double* __restrict__ out, int64_t ldo,
@@ -1050,7 +1075,20 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
             }
 #pragma unroll
             for (int c = 0; c < CPL; ++c) acc[c] = acc[c] + coef * tp[c];
+            if (SEG) {                              // segment ends: store its sum, restart
+                const int sg = __ldg(pl.seg_id + t);
+                if (t + 1 == pl.T || __ldg(pl.seg_id + t + 1) != sg) {
+                    double* o = out + (int64_t)sg * pl.seg_stride + p * ldo;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        const int64_t col = col0 + 32 * c;
+                        if (col < NF) o[col] = accumulate ? o[col] + scale * acc[c] : scale * acc[c];
+                        acc[c] = 0.0;
+                    }
+                }
+            }
         }
+        if (SEG) continue;
         double* o = out + p * ldo;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -1061,6 +1099,30 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
             }
         }
     }
+}
+
+// sumsq[s] = sum over the P x NF values of segment s of v^2, in a fixed order (thread-strided
+// partial sums, then a shared-memory tree): the mean-square norm of the Gerstner-Griebel
+// indicators without a device -> host copy of the surpluses.
+__global__ void __launch_bounds__(256)
+segment_sumsq_kernel(const double* __restrict__ vals, int64_t P, int64_t NF, int64_t ld,
+                     int64_t seg_stride, double* __restrict__ sumsq) {
+    __shared__ double part[256];
+    const double* v = vals + (int64_t)blockIdx.x * seg_stride;
+    const int64_t total = P * NF;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < total; i += 256) {
+        const int64_t r = i / NF, c = i - r * NF;
+        const double a = v[r * ld + c];
+        acc = acc + a * a;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if ((int)threadIdx.x < h) part[threadIdx.x] = part[threadIdx.x] + part[threadIdx.x + h];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sumsq[blockIdx.x] = part[0];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -70,7 +70,15 @@ class ShardedInterpolant:
             plan = self.it.device_plan(x.device.index)
         else:
             plan = self._terms_plan(x.device.index, t0, t1)
+        # same checks as SGInterpolant.interpolate: operator constraints before the launch, the
+        # row count of f against the grid, the pw-quadratic condition flag after it
+        self.it._check_operator_constraints()
+        if f.shape[0] < self.it.num_nodes:
+            raise IndexError(f"f_on_SG has {f.shape[0]} rows, the sparse grid {self.it.num_nodes}")
         out = plan.eval(x, f)
+        if plan.kind == 1 and plan.take_flags() & 1:
+            raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
+                             "(or is NaN)")
         return out
 
     def _terms_plan(self, device, t0, t1):

@@ -1,21 +1,26 @@
-"""Multilevel sparse-grid interpolation evaluated as ONE fused signed combination on the GPU.
+"""Multilevel sparse-grid interpolation evaluated as ONE fused launch on the GPU.
 
 Same class and method names as the reference's sgmethods/multilevel_interpolant.py
 (MLInterpolant :13-169: sample :56, interpolate :89, get_ml_terms :116, total_cost :152).
-The reference file is broken as shipped (it calls sampleOnSG / oldXx / numNodes, which do
-not exist); this module implements the behaviour its docstrings
-and code structure describe:
+The reference file raises AttributeError as shipped (it calls sampleOnSG / oldXx / numNodes,
+SURVEY.md Appendix B.1); its code runs unmodified on objects that carry those names as
+aliases, and the outputs of such runs are this module's parity fixtures
+(tests/golden/ml_*.npz, tests/golden/make_golden.py):
 
     u_ML^K = sum_{k=0}^{K} (I_{K-k} - I_{K-k-1}) u_k ,      I_{-1} = 0,
 
 with ``interp_seq[k]`` the single-level interpolants of increasing resolution and
 ``ml_samples_f[k]`` the samples of u_k on the sparse grid of ``interp_seq[K-k]``.
 
-B200 design: the restriction of level-k samples to the coarser grid (the reference does it
-with ``sample_on_SG(f_mock, old_xx=SG_k, old_samples=...)``, i.e. a row selection) is
-folded into the node maps of the coarser plan (map composition, no data copy), and all
-1 + 2K single-level evaluations run through ``sgm_eval_signed_sum`` on one stream,
-accumulating into the output in place of the reference's (P, NF) temporaries.
+B200 design: the 1 + 2K single-level evaluations of the reference (:103-114) become ONE
+plan and ONE ``sgm_eval`` launch.  The term tables of all parts are concatenated (signed
+combination coefficients, knot families deduplicated), the sample arrays are stacked into
+one device matrix, and the restriction of level-k samples to the coarser grid (the
+reference's ``sample_on_SG(f_mock, old_xx=SG_k, old_samples=...)``, a row selection) is
+composed into the node maps of the coarser part -- no copy, and the bracket tables of a point
+are built once for all parts instead of once per part.  The fused sum runs over all terms
+in one chain, which re-associates the reference's ``out += I_k - I_{k-1}`` (a few ulp of the
+partial sums; the fixtures are met to 1e-12).
 """
 import numpy as np
 
@@ -31,6 +36,7 @@ class MLInterpolant:
         self.n_levels = len(interpolants_sequence)
         self.interp_seq = interpolants_sequence
         self._restricted = {}
+        self._plans = {}
 
     # ----------------------------------------------------------------------------- sampling
     def sample(self, f_approx):
@@ -45,81 +51,141 @@ class MLInterpolant:
         return ml_samples_f
 
     # --------------------------------------------------------------------------- evaluation
-    def _restricted_plan(self, coarse, fine, device):
-        """Device plan of ``interp_seq[coarse]`` whose node maps point into the rows of the
-        samples given on the grid of ``interp_seq[fine]`` (nested grids required)."""
-        from ._device import DevicePlan
-        key = (coarse, fine, device)
+    def _restriction(self, coarse, fine):
+        """For every node of ``interp_seq[coarse]`` the row of the samples given on the grid of
+        ``interp_seq[fine]`` (-1: no such node), found as the reference's ``sample_on_SG``
+        finds recyclable samples (sparse_grid_interpolant.py:195-231): the finer grid is
+        zero-padded, or truncated to the rows whose (int-truncated) tail 1-norm is 0."""
+        key = (coarse, fine)
         if key not in self._restricted:
             ic, jf = self.interp_seq[coarse], self.interp_seq[fine]
-            sel = _lib.match_rows(ic.SG, jf.SG if jf.N == ic.N else _embed(jf.SG, ic.N))
-            if (sel < 0).any():
-                # the reference's f_mock divides by zero when a coarse node is missing (:107)
-                raise ZeroDivisionError("multilevel interpolation needs nested sparse grids: "
-                                        "a node of the coarser grid is not in the finer one")
-            self._restricted[key] = DevicePlan(
-                ic._kind, ic.N, jf.num_nodes, ic._coeffs.astype(np.float64), ic._term_fam,
-                ic._map_off, sel[ic._maps].astype(np.int32), ic._fam_off, ic._fam_knots,
-                device=device)
+            old_xx, rows = jf.SG, np.arange(jf.num_nodes, dtype=np.int64)
+            if old_xx.shape[1] < ic.N:
+                old_xx = np.hstack((old_xx, np.zeros((old_xx.shape[0], ic.N - old_xx.shape[1]))))
+            elif old_xx.shape[1] > ic.N:
+                tail = np.linalg.norm(old_xx[:, ic.N:], ord=1, axis=1).astype(int)
+                rows = np.where(tail == 0)[0]
+                old_xx = old_xx[rows, :ic.N]
+            match = _lib.match_rows(ic.SG, old_xx)          # AssertionError on several matches
+            self._restricted[key] = np.where(match >= 0, rows[np.maximum(match, 0)], -1)
         return self._restricted[key]
 
-    def _signed_sum(self, parts, yy):
-        """parts: list of (interpolant index, restricted-from index or None, sign, samples)."""
-        from ._device import signed_sum, torch_cuda
+    def _fused_plan(self, parts, device, missing):
+        """ONE device plan for ``sum_i sign_i * I_{idx_i}[samples block b_i]``.
+        parts: tuple of (interpolant index, restricted-from index or None, sign, block id);
+        block b holds samples given on the grid of interpolant ``block_grid[b]`` and starts at
+        row ``block_off[b]`` of the stacked sample matrix.  ``missing``: "raise" (a coarse
+        node without a match raises ZeroDivisionError, like the reference's f_mock of
+        ``interpolate``, :107-108) or "zero" (it reads a zero row, like the f_mock of
+        ``get_ml_terms``, :142-143)."""
+        from ._device import DevicePlan
+        key = (parts, device, missing)
+        if key in self._plans:
+            return self._plans[key]
+        seq = self.interp_seq
+        kinds = {seq[i]._kind for i, _, _, _ in parts}
+        if len(kinds) != 1:
+            raise NotImplementedError("the interpolants of a multilevel sequence must share "
+                                      "their tensor-product operator")
+        n_max = max(seq[i].N for i, _, _, _ in parts)
+        block_grid, block_off, total = {}, {}, 0
+        for i, fine, _, b in parts:
+            grid = i if fine is None else fine
+            assert block_grid.setdefault(b, grid) == grid
+        for b in sorted(block_grid):
+            block_off[b] = total
+            total += seq[block_grid[b]].num_nodes
+        zero_row = total                                    # one extra row of zeros
+        fam_index, fam_list = {}, []
+        coeffs, term_fam, maps, map_sizes = [], [], [], []
+        for i, fine, sign, b in parts:
+            it = seq[i]
+            it._check_operator_constraints()
+            lut = np.empty(max(len(it._fam_knots_list), 1), dtype=np.int32)
+            for j, g in enumerate(it._fam_knots_list):      # knot families deduplicated by value
+                k = g.tobytes()
+                if k not in fam_index:
+                    fam_index[k] = len(fam_list)
+                    fam_list.append(g)
+                lut[j] = fam_index[k]
+            tf = np.full((it._term_fam.shape[0], n_max), -1, dtype=np.int32)
+            tf[:, :it.N] = np.where(it._term_fam >= 0, lut[np.maximum(it._term_fam, 0)], -1)
+            term_fam.append(tf)
+            coeffs.append(sign * it._coeffs.astype(np.float64))
+            if fine is None:
+                rows = it._maps.astype(np.int64) + block_off[b]
+            else:
+                sel = self._restriction(i, fine)
+                if (sel < 0).any() and missing == "raise":
+                    raise ZeroDivisionError("multilevel interpolation needs nested sparse grids: "
+                                            "a node of the coarser grid is not in the finer one")
+                rows = np.where(sel >= 0, sel + block_off[b], zero_row)[it._maps]
+            maps.append(rows.astype(np.int32))
+            map_sizes.append(np.diff(it._map_off))
+        map_off = np.concatenate(([0], np.cumsum(np.concatenate(map_sizes)))).astype(np.int64)
+        fam_off = np.concatenate(([0], np.cumsum([g.size for g in fam_list]))).astype(np.int64)
+        plan = DevicePlan(kinds.pop(), n_max, total + 1, np.concatenate(coeffs),
+                          np.concatenate(term_fam), map_off, np.concatenate(maps), fam_off,
+                          np.concatenate(fam_list) if fam_list else np.zeros(0), device=device)
+        self._plans[key] = (plan, [block_off[b] for b in sorted(block_off)], total + 1, n_max)
+        return self._plans[key]
+
+    def _evaluate(self, parts, blocks, yy, missing):
+        """parts as in ``_fused_plan``; blocks: list of sample arrays (block id = position)."""
+        from ._device import torch_cuda
         from .sparse_grid_interpolant import _to_device
         torch = torch_cuda()
         as_torch = isinstance(yy, torch.Tensor)
         device = yy.device if as_torch and yy.is_cuda else \
             torch.device("cuda", torch.cuda.current_device())
+        plan, offs, rows, n_max = self._fused_plan(tuple(parts), device.index, missing)
         x = _to_device(torch, yy, device)
         if x.dim() == 1:
             x = x.reshape(-1, 1)
-        n_max = max(self.interp_seq[i].N for i, _, _, _ in parts)
         if x.shape[1] < n_max:
             raise IndexError(f"yy has {x.shape[1]} columns, the interpolants use {n_max}")
-        plans, signs, fs, cache = [], [], [], {}
-        for idx, fine, sign, samples in parts:
-            it = self.interp_seq[idx]
-            it._check_operator_constraints()
-            plans.append(it.device_plan(device.index) if fine is None
-                         else self._restricted_plan(idx, fine, device.index))
-            if id(samples) not in cache:
-                cache[id(samples)] = _to_device(torch, samples, device)
-            fs.append(cache[id(samples)])
-            signs.append(sign)
-        out = signed_sum(plans, signs, x, fs)
-        for it_idx, _, _, _ in parts:
-            it = self.interp_seq[it_idx]
-            if it._kind == _lib.KIND_QUADRATIC:
-                for p in plans:
-                    if p.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
-                        raise IndexError("pw-quadratic interpolation: a point lies right of the "
-                                         "last knot (or is NaN)")
-                break
-        return out if as_torch else out.cpu().numpy()
+        fs = [_to_device(torch, np.atleast_2d(s) if not isinstance(s, torch.Tensor) else s, device)
+              for s in blocks]
+        NF = fs[0].shape[1]
+        F = torch.zeros((rows, NF), dtype=torch.float64, device=device)   # last row stays 0
+        for off, f, (_, grid) in zip(offs, fs, sorted(self._block_grids(parts).items())):
+            if f.shape != (self.interp_seq[grid].num_nodes, NF):
+                raise IndexError(f"samples of shape {tuple(f.shape)} given for a sparse grid with "
+                                 f"{self.interp_seq[grid].num_nodes} nodes and {NF} outputs")
+            F[off:off + f.shape[0]] = f
+        out = plan.eval(x, F)
+        if plan.kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
+            raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
+                             "(or is NaN)")
+        # the reference returns np.squeeze'd arrays (every SGInterpolant.interpolate does, :279)
+        return out.squeeze() if as_torch else np.squeeze(out.cpu().numpy())
+
+    @staticmethod
+    def _block_grids(parts):
+        return {b: (i if fine is None else fine) for i, fine, _, b in parts}
 
     def interpolate(self, yy, ml_samples_f):
         """Multilevel interpolant at the rows of ``yy``:
         I_0[s_K] + sum_{k=1}^{K} ( I_k[s_{K-k}] - I_{k-1}[s_{K-k} restricted] ), s = samples
-        (reference :103-114).  Returns a (P, NF) array."""
+        (reference :103-114), in one fused launch.  Returns the squeezed (P, NF) array."""
         K = self.n_levels - 1
-        parts = [(0, None, 1.0, ml_samples_f[K])]
+        parts, blocks = [(0, None, 1.0, 0)], [ml_samples_f[K]]
         for k in range(1, self.n_levels):
-            s = ml_samples_f[K - k]
-            parts.append((k, None, 1.0, s))
-            parts.append((k - 1, k, -1.0, s))
-        return self._signed_sum(parts, yy)
+            parts.append((k, None, 1.0, k))
+            parts.append((k - 1, k, -1.0, k))
+            blocks.append(ml_samples_f[K - k])
+        return self._evaluate(parts, blocks, yy, "raise")
 
     def get_ml_terms(self, yy, ml_samples_f):
         """The multilevel terms one by one: entry k = (I_{K-k} - I_{K-k-1})[u_k], the last one
-        without subtraction (reference :135-150)."""
+        without subtraction (reference :135-150); one fused launch per term."""
         ml_terms = []
         for k in range(self.n_levels):
             lev = self.n_levels - 1 - k
-            parts = [(lev, None, 1.0, ml_samples_f[k])]
+            parts = [(lev, None, 1.0, 0)]
             if k < self.n_levels - 1:
-                parts.append((lev - 1, lev, -1.0, ml_samples_f[k]))
-            ml_terms.append(self._signed_sum(parts, yy))
+                parts.append((lev - 1, lev, -1.0, 0))
+            ml_terms.append(self._evaluate(parts, [ml_samples_f[k]], yy, "zero"))
         return ml_terms
 
     def total_cost(self, cost_kk):
@@ -129,13 +195,6 @@ class MLInterpolant:
         for k in range(self.n_levels):
             total += self.interp_seq[k].num_nodes * cost_kk[self.n_levels - k - 1]
         return total
-
-
-def _embed(SG, N):
-    """Rows of SG zero-padded (or truncated, if the tail is zero) to N columns."""
-    if SG.shape[1] < N:
-        return np.hstack((SG, np.zeros((SG.shape[0], N - SG.shape[1]))))
-    return SG[:, :N]
 
 
 # BASELINE.json calls the class MultilevelInterpolant

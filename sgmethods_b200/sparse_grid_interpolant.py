@@ -237,33 +237,37 @@ class SGInterpolant:
         P, NF = x_host.shape[0], f.shape[1]
         out = torch.empty((P, NF), dtype=torch.float64, device=device)
         compute = torch.cuda.current_stream(device)
-        copier = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device)
-        copier.wait_stream(compute)
         is_numpy = isinstance(x_host, np.ndarray)
-        if is_numpy:
-            if getattr(self, "_staging", None) is None:
-                self._staging = [torch.empty((_H2D_CHUNK, self.N), dtype=torch.float64).pin_memory()
-                                 for _ in range(2)]
-                self._staging_free = [None, None]      # event: the buffer's last H2D copy is done
-        # two persistent device chunk buffers per device (double buffering): no allocator
-        # traffic inside the loop -- chunk tensors allocated on the copy stream and handed to
-        # the compute stream made the caching allocator fall back to cudaMalloc on some runs
-        # (end-to-end time bimodal, 26 / 42 ms on config 2)
-        key = device.index
-        chunks = getattr(self, "_dev_chunks", None)
-        if chunks is None:
-            chunks = self._dev_chunks = {}
-        if key not in chunks:
-            chunks[key] = ([torch.empty((_H2D_CHUNK, self.N), dtype=torch.float64, device=device)
-                            for _ in range(2)], [None, None])
-        dev_buf, dev_free = chunks[key]          # dev_free[b]: event, last evaluation from buffer b
+        # Everything the pipeline keeps between calls is PER DEVICE: the copy stream, the two
+        # pinned staging buffers (numpy input) with the events of their last H2D copy, and two
+        # persistent device chunk buffers (double buffering; no allocator traffic inside the
+        # loop -- chunk tensors allocated on the copy stream and handed to the compute stream
+        # made the caching allocator fall back to cudaMalloc on some runs: end-to-end time
+        # bimodal, 26 / 42 ms on config 2).
+        pipes = getattr(self, "_pipes", None)
+        if pipes is None:
+            pipes = self._pipes = {}
+        st = pipes.get(device.index)
+        if st is None:
+            st = pipes[device.index] = {
+                "copier": torch.cuda.Stream(device),
+                "dev_buf": [torch.empty((_H2D_CHUNK, self.N), dtype=torch.float64, device=device)
+                            for _ in range(2)],
+                "dev_free": [None, None],        # event: last evaluation reading the buffer
+                "staging": None, "staging_free": [None, None]}
+        if is_numpy and st["staging"] is None:
+            st["staging"] = [torch.empty((_H2D_CHUNK, self.N), dtype=torch.float64).pin_memory()
+                             for _ in range(2)]
+        copier, dev_buf, dev_free = st["copier"], st["dev_buf"], st["dev_free"]
+        staging, staging_free = st["staging"], st["staging_free"]
+        copier.wait_stream(compute)
         for i, lo in enumerate(range(0, P, _H2D_CHUNK)):
             hi = min(P, lo + _H2D_CHUNK)
             b = i % 2
             if is_numpy:
-                buf = self._staging[b]
-                if self._staging_free[b] is not None:
-                    self._staging_free[b].synchronize()
+                buf = staging[b]
+                if staging_free[b] is not None:
+                    staging_free[b].synchronize()
                 src = buf[:hi - lo]
                 np.copyto(src.numpy(), x_host[lo:hi, :self.N], casting="same_kind")
             else:
@@ -276,7 +280,7 @@ class SGInterpolant:
                 done = torch.cuda.Event()
                 done.record(copier)
             if is_numpy:
-                self._staging_free[b] = done
+                staging_free[b] = done
             # enqueue the evaluation of this chunk right away so that it overlaps the host
             # side staging copy of the next one
             compute.wait_event(done)

@@ -57,3 +57,52 @@ def unpack_plan(g):
     maps = [g["maps"][g["map_off"][t]:g["map_off"][t + 1]].reshape(shapes[t])
             for t in range(T)]
     return dims, shapes, maps
+
+
+# ------------------------------------------------------------------ composite drivers
+# Multilevel cases (make_golden.drivers): name -> (knot family, lev2knots, kind, levels, NF,
+# points, seed).  Level k of a case uses the multi-index set ml_mid_set(mis, name, k).
+ML_CASES = {
+    "ml_lin_nf1": ("cc", "doubling", "linear", 4, 1, 160, 101),
+    "ml_quad_nf3": ("equi_arr", "doubling", "quadratic", 4, 3, 120, 102),
+    # the parametric dimension grows with the level (N = 2, 3, 4): the restriction to the
+    # coarser grid drops the rows of the finer grid whose tail is non-zero
+    # (sparse_grid_interpolant.py:205-212); the newest directions carry level <= 1 so that
+    # the reference's int-truncated tail test is exact
+    "ml_lin_grow": ("cc", "doubling", "linear", 3, 2, 96, 103),
+}
+
+
+def ml_mid_set(mis, name, k):
+    if name == "ml_lin_grow":
+        return mis.aniso_smolyak_mid_set(k + 1, k + 2, [1, 1, 2, 3][:k + 2])
+    if name == "ml_quad_nf3":
+        return mis.smolyak_mid_set(k, 3)
+    return mis.smolyak_mid_set(k, 4)
+
+
+def ML_F_APPROX(y, k):
+    """Level-k 'finite element' approximation used for MLInterpolant.sample."""
+    return np.array([np.sin(np.sum(y)) + 2.0 ** (-k), float(k) + y[0]])
+
+
+# Indicator cases: name -> (knot family, lev2knots, kind, script, points, seed); the script is
+# a list of adaptive steps, each a list of MidSet operations ("e", margin index) / ("d", None)
+# applied before the indicators of that step are computed (old reduced margin = previous
+# step's, so steps >= 1 exercise the recycling and the dimension growth).
+GG_CASES = {
+    "gg_lin_unb": ("unb", "2^(n+1)-1", "linear",
+                   [[("e", 0), ("d", None), ("e", 1), ("e", 0), ("d", None), ("e", 2)],
+                    [("e", 0)], [("d", None), ("e", 3)]], 300, 201),
+    "gg_quad_equi": ("equi_arr", "doubling", "quadratic",
+                     [[("e", 0), ("d", None), ("e", 1), ("e", 0)], [("d", None), ("e", 1)]],
+                     200, 202),
+}
+
+
+def GG_F(y):
+    return np.array([np.exp(-0.3 * np.sum(y * y)), np.sum(y)])
+
+
+def GG_NORM(a, b):
+    return float(np.sqrt(np.mean(np.sum((a - b) ** 2, axis=1))))

@@ -18,6 +18,7 @@ from conftest import load_golden
 from golden_cases import CASES, LEV2KNOTS, knot_family
 from oracle import brownian_oracle, sg_oracle
 from sgmethods_b200 import multi_index_sets as mis, nodes_1d
+from sgmethods_b200._device import reload_knobs
 from sgmethods_b200.parametric_expansions_brownian_motion import (param_KL_Brownian_motion,
                                                                    param_LC_Brownian_motion)
 from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
@@ -396,12 +397,12 @@ def test_multilevel_interpolant_against_oracle(kind, NF):
         p.SG = it.SG
     ref = drivers_oracle.ml_interpolate(plans, kind, yy, ml)
     got = mli.interpolate(yy, ml)
-    assert rel_err(got, ref) <= TOL
+    assert rel_err(got, np.squeeze(ref)) <= TOL
     ref_terms = drivers_oracle.ml_terms(plans, kind, yy, ml)
     got_terms = mli.get_ml_terms(yy, ml)
     assert len(got_terms) == 4
     for a, b in zip(got_terms, ref_terms):
-        assert rel_err(a, b) <= TOL
+        assert rel_err(a, np.squeeze(b)) <= TOL
     assert mli.total_cost(np.array([1., 10., 100., 1000.])) == \
         sum(seq[k].num_nodes * [1., 10., 100., 1000.][3 - k] for k in range(4))
 
@@ -456,6 +457,68 @@ def test_error_indicators_against_oracle():
                                      lambda y: (calls.append(1), f(y))[1], cur.SG, u_on_SG, yy,
                                      norm, u_interp)
     assert np.array_equal(again[:-1], got[:-1] + 1.0) and abs(again[-1] - got[-1]) < 1e-14
+
+
+# Reference-pinned: fixtures ml_*.npz / gg_*.npz are outputs of the reference's own driver code
+# (run on alias subclasses, tests/golden/make_golden.py).
+@pytest.mark.parametrize("name", ["ml_lin_nf1", "ml_quad_nf3", "ml_lin_grow"])
+def test_multilevel_against_reference_driver_outputs(name):
+    from golden_cases import ML_CASES, ML_F_APPROX, ml_mid_set
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    fam, l2k, kind, levels, NF, P, seed = ML_CASES[name]
+    g = load_golden(name)
+    seq = [SGInterpolant(np.asarray(ml_mid_set(mis, name, k)), knot_family(fam, nodes_1d),
+                         LEV2KNOTS[l2k], tp_interpolant=KIND_CLASS[kind], verbose=False)
+           for k in range(levels)]
+    for k, it in enumerate(seq):
+        assert it.SG.tobytes() == g[f"SG_{k}"].tobytes()
+    mli = MLInterpolant(seq)
+    ml = [g[f"ml_{k}"] for k in range(levels)]
+    out = mli.interpolate(g["yy"], ml)
+    assert out.shape == g["out"].shape                     # squeezed like the reference
+    assert rel_err(out, g["out"]) <= TOL
+    terms = mli.get_ml_terms(g["yy"], ml)
+    assert len(terms) == levels
+    for k in range(levels):
+        assert rel_err(terms[k], g[f"term_{k}"]) <= TOL
+    sampled = mli.sample(ML_F_APPROX)
+    for k in range(levels):
+        assert np.array_equal(sampled[k], g[f"sampled_{k}"])
+    assert rel_err(mli.interpolate(g["yy"], sampled), g["out_sampled"]) <= TOL
+    assert mli.total_cost(np.arange(1., levels + 1.)) == float(g["cost"])
+
+
+@pytest.mark.parametrize("name", ["gg_lin_unb", "gg_quad_equi"])
+@pytest.mark.parametrize("method", ["surplus", "rebuild", "surplus_gpu_norm"])
+def test_error_indicators_against_reference_driver_outputs(name, method):
+    from golden_cases import GG_CASES, GG_F, GG_NORM
+    from sgmethods_b200.compute_error_indicators import MeanSquareNorm, compute_GG_indicators_RM
+    norm = GG_NORM
+    if method == "surplus_gpu_norm":     # same norm, reduced on the GPU (sgm_surplus_norms)
+        method, norm = "surplus", MeanSquareNorm()
+    from sgmethods_b200.mid_set import MidSet
+    fam, l2k, kind, script, P, seed = GG_CASES[name]
+    g = load_golden(name)
+    knots, lev = knot_family(fam, nodes_1d), LEV2KNOTS[l2k]
+    ms = MidSet(track_reduced_margin=True)
+    for step, ops in enumerate(script):
+        for op, arg in ops:
+            ms.enlarge_from_margin(arg) if op == "e" else ms.increase_dim()
+        assert np.array_equal(ms.reduced_margin, g[f"rm_{step}"])
+        calls = []
+
+        def f_count(y):
+            calls.append(1)
+            return GG_F(y)
+        est = compute_GG_indicators_RM(
+            g[f"old_rm_{step}"], g[f"old_est_{step}"], ms, knots, lev, f_count, g[f"SG_{step}"],
+            g[f"u_on_SG_{step}"], g[f"yy_{step}"], norm, g[f"u_interp_{step}"],
+            TP_inteporlant=KIND_CLASS[kind], method=method)
+        ref = g[f"est_{step}"]
+        scale = max(1.0, float(np.max(np.abs(g[f"u_interp_{step}"]))))
+        assert est.shape == ref.shape
+        assert np.max(np.abs(est - ref)) <= 1e-12 * scale, (step, np.max(np.abs(est - ref)))
+        assert len(calls) <= int(g[f"n_f_calls_{step}"])     # never more samples than the reference
 
 
 def test_pipelined_host_path_equals_device_path():
@@ -548,8 +611,10 @@ def test_two_points_per_warp_wide_kernel_equals_one_point_kernel_and_oracle(kind
     f = rng.normal(size=(it.num_nodes, NF))
     got = it.interpolate(x, f)
     monkeypatch.setenv("SGM_WIDE_PAIRS", "0")
+    reload_knobs()
     one = it.interpolate(x, f)
     monkeypatch.delenv("SGM_WIDE_PAIRS")
+    reload_knobs()
     assert np.array_equal(got, one, equal_nan=True)
     pick = np.concatenate([rng.choice(P, 40, replace=False), [P - 1]])
     ref = sg_oracle.interpolate(oracle_plan_of(it), x[pick], f, kind, squeeze=False)
@@ -644,10 +709,15 @@ def test_prefix_kernel_equals_split_kernel_and_oracle(run, monkeypatch):
             if run.endswith("u"):
                 monkeypatch.setenv("SGM_PREFIX_UNBALANCED", "1")
             monkeypatch.setenv("SGM_FORCE_KERNEL", "prefix")
+            reload_knobs()
             got = it.interpolate(x, f)
             monkeypatch.setenv("SGM_FORCE_KERNEL", "split")
+            reload_knobs()
             old = it.interpolate(x, f)
             monkeypatch.delenv("SGM_FORCE_KERNEL")
+            for name in ("SGM_PREFIX_RUN", "SGM_PREFIX_PPL", "SGM_PREFIX_UNBALANCED"):
+                monkeypatch.delenv(name, raising=False)
+            reload_knobs()
             default = it.interpolate(x, f)
             assert np.array_equal(got, old, equal_nan=True)
             assert np.array_equal(default, old, equal_nan=True)

@@ -206,3 +206,17 @@ def test_nodes_bit_exact_against_reference_outputs():
 def test_tp_knots():
     kk = tp_knots(n1d.cc_nodes, np.array([3, 1, 5]))
     assert len(kk) == 3 and kk[1] == 0 and kk[2].shape == (5,)
+
+
+@pytest.mark.parametrize("name", ["gg_lin_unb", "gg_quad_equi"])
+def test_midset_replay_of_the_indicator_fixture_scripts(name):
+    """The adaptive scripts behind tests/golden/gg_*.npz (reference MidSet) give the same
+    multi-index sets and reduced margins with this repo's MidSet."""
+    from golden_cases import GG_CASES
+    g = load_golden(name)
+    ms = MidSet(track_reduced_margin=True)
+    for step, ops in enumerate(GG_CASES[name][3]):
+        for op, arg in ops:
+            ms.enlarge_from_margin(arg) if op == "e" else ms.increase_dim()
+        assert same(ms.mid_set, g[f"mid_{step}"])
+        assert same(ms.reduced_margin, g[f"rm_{step}"])

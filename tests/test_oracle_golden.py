@@ -129,3 +129,55 @@ def test_brownian_matches_reference():
     assert np.array_equal(got, g["kl_W"])
     assert [brownian_oracle.level_lc(i) for i in range(6)] == \
         [(0, 1), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+
+
+# ---------------------------------------------------------------- composite drivers (a12, a14)
+# Fixtures ml_*.npz / gg_*.npz are outputs of the reference's OWN driver code
+# (multilevel_interpolant.py:89-150, compute_error_indicators.py:78-121) run on alias
+# subclasses that carry the camelCase names it calls (tests/golden/make_golden.py).
+def ml_oracle_plans(name):
+    from golden_cases import ML_CASES, ml_mid_set
+    from sgmethods_b200 import multi_index_sets as mis
+    fam, l2k, kind, levels, NF, P, seed = ML_CASES[name]
+    knots = knot_family(fam, nodes_1d)
+    plans = [sg_oracle.make_plan(np.asarray(ml_mid_set(mis, name, k)), knots, LEV2KNOTS[l2k])
+             for k in range(levels)]
+    return plans, kind, levels
+
+
+@pytest.mark.parametrize("name", ["ml_lin_nf1", "ml_quad_nf3", "ml_lin_grow"])
+def test_multilevel_oracle_matches_reference_driver(name):
+    from oracle import drivers_oracle
+    g = load_golden(name)
+    plans, kind, levels = ml_oracle_plans(name)
+    for k, p in enumerate(plans):
+        assert p.SG.tobytes() == g[f"SG_{k}"].tobytes()
+    ml = [g[f"ml_{k}"] for k in range(levels)]
+    out = drivers_oracle.ml_interpolate(plans, kind, g["yy"], ml)
+    assert np.array_equal(np.squeeze(out), g["out"])
+    for k, term in enumerate(drivers_oracle.ml_terms(plans, kind, g["yy"], ml)):
+        assert np.array_equal(np.squeeze(term), g[f"term_{k}"]), k
+    sampled = [g[f"sampled_{k}"] for k in range(levels)]
+    out_s = drivers_oracle.ml_interpolate(plans, kind, g["yy"], sampled)
+    assert np.array_equal(np.squeeze(out_s), g["out_sampled"])
+
+
+@pytest.mark.parametrize("name", ["gg_lin_unb", "gg_quad_equi"])
+def test_indicator_oracle_matches_reference_driver(name):
+    from golden_cases import GG_CASES, GG_F, GG_NORM
+    from oracle import drivers_oracle
+    fam, l2k, kind, script, P, seed = GG_CASES[name]
+    g = load_golden(name)
+    knots = knot_family(fam, nodes_1d)
+    for step in range(int(g["steps"])):
+        calls = []
+
+        def f_count(y):
+            calls.append(1)
+            return GG_F(y)
+        est = drivers_oracle.gg_indicators(
+            g[f"mid_{step}"], g[f"rm_{step}"], knots, LEV2KNOTS[l2k], f_count, g[f"SG_{step}"],
+            g[f"u_on_SG_{step}"], g[f"yy_{step}"], GG_NORM, g[f"u_interp_{step}"], kind,
+            old_RM=g[f"old_rm_{step}"], old_estimators=g[f"old_est_{step}"])
+        assert np.array_equal(est, g[f"est_{step}"]), (step, est - g[f"est_{step}"])
+        assert len(calls) == int(g[f"n_f_calls_{step}"])
