@@ -103,6 +103,19 @@ int sgm_grid_copy_nodes_dense(const sgm_grid* g, double* SG);
 int sgm_grid_copy_nodes_csr(const sgm_grid* g, int64_t* row_off, int32_t* cols, double* vals);
 void sgm_grid_destroy(sgm_grid* g);
 
+/* Tables of the grouped hierarchical-surplus kernel (kind SGM_HIER_PW_LINEAR; layout in
+ * csrc/sgm_hier_host.cpp), exposed so that CPU tests can check them without a GPU.
+ *   term_fam T x N (family per direction, -1 inactive), fam_extent n_fam (new knots per
+ *   family), val_off T (offset of every term's surplus block, first direction fastest).
+ * Call with groups = parents = steps = hmap = NULL to get the sizes: groups 12 and parents 8 ints
+ * per group, steps 2 ints each, hmap n_slots ints (value slot of the kernel's layout -> index
+ * in the caller's layout, -1 = padding); root_slot = slot of the zero multi-index.
+ * SGM_ERR_INVALID if the set is not downward closed. */
+int sgm_host_hier_groups(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
+                         const int32_t* fam_extent, const int64_t* val_off,
+                         int64_t* n_groups, int64_t* n_steps, int64_t* n_slots, int32_t* root_slot,
+                         int32_t* groups, int32_t* parents, int32_t* steps, int32_t* hmap);
+
 /* Row matching used by sample_on_SG's recycling (sparse_grid_interpolant.py:214-231): for
  * every row of `xx` (n x N) the index of the unique row of `old_xx` (n_old x N) with
  * 1-norm distance < tol, or -1.  Returns SGM_ERR_INVALID if a row has several matches

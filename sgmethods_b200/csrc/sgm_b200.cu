@@ -17,6 +17,12 @@ namespace {
 thread_local std::string g_last_error;
 }
 
+// sgm_hier_host.cpp
+bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
+                           const int* fam_extent, const int64_t* val_off,
+                           std::vector<int>& groups, std::vector<int>& parents,
+                           std::vector<int>& steps, std::vector<int>& hmap, int* root_slot);
+
 int sgm_fail(int code, const char* msg) {
     g_last_error = msg ? msg : "";
     return code;
@@ -54,6 +60,7 @@ struct Knobs {
     bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false;
     int wide_pairs = -1;         // SGM_WIDE_PAIRS: -1 = automatic, 0 | 1
     long long col_loop_max = -1; // SGM_COL_LOOP_MAX
+    int h2_shape = 0;            // SGM_H2_SHAPE: first launch shape of the grouped hierarchical kernel
     static Knobs from_env() {
         Knobs k;
         if (const char* v = std::getenv("SGM_FORCE_KERNEL"))
@@ -68,6 +75,7 @@ struct Knobs {
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
         if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
         if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
+        if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 3;
         return k;
     }
 };
@@ -84,6 +92,7 @@ struct sgm_plan {
     bool prefix_ok = false;      // tables of the prefix kernel (pw-linear, all packed) are built
     int prefix_wins = 0;         // occupancy comparison prefix vs split kernel (plan creation)
     bool prefix_launch_ok = false;
+    bool h2_ok = false;          // tables of the grouped hierarchical kernel are built
     int64_t table_bytes = 0;
     int kmax = 0;
     int max_entry_n = 0;         // largest knot family among the table entries
@@ -169,6 +178,14 @@ PointLaunch choose_point_launch(const sgm_plan* plan) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// bytes of the pre-gathered value table at the head of the workspace (the grouped hierarchical
+// kernel has its own, padded layout)
+size_t g_bytes_of(const sgm_plan* plan) {
+    return align_up((size_t)std::max<int64_t>(plan->n_vals, plan->dev.h2_n_vals) * 8, 256);
+}
+bool use_h2_kernel(const sgm_plan* plan) {
+    return plan->dev.kind == SGM_HIER_PW_LINEAR && plan->h2_ok && !plan->knobs.no_h2;
+}
 constexpr int64_t kSortMinPoints = 32768;       // scalar kernels
 constexpr int64_t kSortMinPointsCols = 4096;    // wide column kernel with two points per warp
 size_t sort_scratch_bytes(int64_t P) {
@@ -360,6 +377,30 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
     {
         int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
         if (rc) return rc;
+    }
+    if (KIND == SGM_HIER_PW_LINEAR && use_h2_kernel(plan)) {
+        // launch shapes of the grouped kernel, best first (dev knob SGM_H2_SHAPE picks one)
+        struct Shape { SplitKernel kern; int warps; };
+        const Shape shapes[3] = {{sgm::eval_hier_groups_kernel<16, 2>, 16},
+                                 {sgm::eval_hier_groups_kernel<8, 3>, 8},
+                                 {sgm::eval_hier_groups_kernel<16, 1>, 16}};
+        const PlanDev& d = plan->dev;
+        for (int si = 0; si < 3; ++si) {
+            const Shape& sh = shapes[(si + plan->knobs.h2_shape) % 3];
+            const size_t smem = (size_t)d.n_knots * 16 + (size_t)d.B * 32 * 8 + (size_t)sh.warps * 32 * 8 +
+                                (size_t)d.E * 32 * 2 + 64 + 16;
+            if (smem > (size_t)plan->max_smem_optin ||
+                cudaFuncSetAttribute(sh.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                continue;
+            int bps = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sh.kern, sh.warps * 32, smem);
+            if (bps < 1) continue;
+            blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * bps);
+            sh.kern<<<(unsigned)blocks, sh.warps * 32, smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+                                                                     scale, accumulate, perm);
+            SGM_CUDA(cudaGetLastError());
+            return SGM_OK;
+        }
     }
     if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !plan->knobs.no_h1) {
         constexpr int HW = 16;
@@ -560,16 +601,17 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
     const int kind = plan->dev.kind;
     // one scalar evaluation (kernel A family) of column `col` of f into column `col` of out
     auto scalar_column = [&](int64_t col) -> int {
-        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        const size_t g_bytes = g_bytes_of(plan);
         if (workspace_bytes < g_bytes || !workspace)
             return sgm_fail(SGM_ERR_WORKSPACE, "eval: workspace too small");
         double* G = static_cast<double*>(workspace);
         unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
-        const int64_t n = plan->n_vals;
+        const bool h2 = use_h2_kernel(plan);
+        const int64_t n = h2 ? plan->dev.h2_n_vals : plan->n_vals;
         const int gblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plan->sm_count * 8);
         const bool prefix = use_prefix_kernel(plan, P);
         sgm::pregather_kernel<<<std::max(gblocks, 1), 256, 0, stream>>>(
-            prefix ? plan->dev.gmaps : plan->dev.maps, n, f + col, ldf, 1, G);
+            h2 ? plan->dev.h2_maps : prefix ? plan->dev.gmaps : plan->dev.maps, n, f + col, ldf, 1, G);
         SGM_CUDA(cudaGetLastError());
         const size_t sb = workspace_bytes - g_bytes;
         double* o = out + col;
@@ -590,7 +632,7 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         // locality permutation of the points for the two-points-per-warp wide kernel (scratch
         // behind the G area, shared with the scalar path: launches are ordered on the stream)
         const int* perm = nullptr;
-        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        const size_t g_bytes = g_bytes_of(plan);
         if (ncols >= 64 && workspace && workspace_bytes > g_bytes + sort_scratch_bytes(P)) {
             int rc = locality_sort(plan, x, P, ldx, static_cast<unsigned char*>(workspace) + g_bytes,
                                    workspace_bytes - g_bytes, stream, &perm, kSortMinPointsCols);
@@ -622,7 +664,7 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         // all columns (its last 256-column tile is guarded), instead of full tiles + a ragged
         // remainder through the narrower kernels (config 4, NF = 1000: 84 -> 67 ms).  A short
         // tail of a packed pw-linear plan still goes column by column through the scalar kernel.
-        const size_t g_bytes = align_up((size_t)plan->n_vals * 8, 256);
+        const size_t g_bytes = g_bytes_of(plan);
         const bool pairs_ok = aligned && plan->dev.n_corners > 0 && NF >= 512 && P >= kSortMinPointsCols &&
                               P < 0x7fffffff && plan->dev.n_key >= 4 && !plan->knobs.no_sort &&
                               plan->knobs.wide_pairs != 0 && workspace &&
@@ -1077,9 +1119,22 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     std::vector<short> newrank;
     if (kind == SGM_HIER_PW_LINEAR)
         for (int64_t i = 0; i < n_knots; ++i) newrank.push_back((short)desc->fam_newrank[i]);
+    // grouped hierarchical kernel: group / step tables over the trie of the multi-indices
+    std::vector<int> h2_groups, h2_parents, h2_steps, h2_maps;
+    int h2_root = -1;
+    if (kind == SGM_HIER_PW_LINEAR && T > 0) {
+        if (sgm_build_hier_groups(T, N, desc->term_fam, desc->n_fam, fam_extent.data(), desc->map_off,
+                                  h2_groups, h2_parents, h2_steps, h2_maps, &h2_root)) {
+            for (int& v : h2_maps)                      // slot -> row of f through the caller's map
+                if (v >= 0) v = desc->maps[v];
+        } else {
+            h2_groups.clear(); h2_parents.clear(); h2_steps.clear(); h2_maps.clear();
+        }
+    }
     std::vector<unsigned> flags(4, 0u);
     int rc = SGM_OK;
     const unsigned* cflags = nullptr;
+    const int* h2g = nullptr; const int* h2p = nullptr;
     if ((rc = upload(plan, hdr, &d.hdr)) || (rc = upload(plan, tdim, &d.tdim)) ||
         (rc = upload(plan, rec, &d.rec)) || (rc = upload(plan, hrec, &d.hrec)) ||
         (rc = upload(plan, coeff, &d.coeff)) || (rc = upload(plan, entries, &d.ent)) ||
@@ -1087,11 +1142,20 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         (rc = upload(plan, gmaps, &d.gmaps)) || (rc = upload(plan, run_start, &d.run_start)) ||
         (rc = upload(plan, corner_term, &d.corner_term)) ||
         (rc = upload(plan, corner_off, &d.corner_off)) || (rc = upload(plan, knots, &d.knots)) ||
-        (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, newrank, &d.newrank)) || (rc = upload(plan, flags, &cflags))) {
+        (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, newrank, &d.newrank)) ||
+        (rc = upload(plan, h2_groups, &h2g)) || (rc = upload(plan, h2_parents, &h2p)) ||
+        (rc = upload(plan, h2_steps, &d.h2_steps)) || (rc = upload(plan, h2_maps, &d.h2_maps)) ||
+        (rc = upload(plan, flags, &cflags))) {
         sgm_plan_destroy(plan);
         return rc;
     }
     d.flags = const_cast<unsigned*>(cflags);
+    d.h2_groups = reinterpret_cast<const int4*>(h2g);
+    d.h2_parents = reinterpret_cast<const int4*>(h2p);
+    d.h2_n_groups = (int)(h2_groups.size() / 12);
+    d.h2_n_vals = (int)h2_maps.size();
+    d.h2_root_off = h2_root;
+    plan->h2_ok = !h2_maps.empty();
     d.seg_id = nullptr;
     d.seg_stride = 0;
     if (desc->n_seg > 0) {
@@ -1153,7 +1217,7 @@ int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags) {
 
 size_t sgm_eval_workspace_bytes(const sgm_plan* plan, int64_t P, int64_t NF) {
     if (!plan) return 256;
-    size_t bytes = align_up((size_t)plan->n_vals * 8, 256);
+    size_t bytes = g_bytes_of(plan);
     const PointLaunch L = choose_point_launch(plan);
     size_t scratch = 0;
     if (L.global_basis) {

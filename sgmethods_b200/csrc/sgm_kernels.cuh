@@ -72,6 +72,14 @@ struct PlanDev {
     const short* newrank;              // SGM_HIER_PW_LINEAR: rank of a knot among the new knots, -1 old
     const TermRec* hrec;               // SGM_HIER_PW_LINEAR: records grouped by number of directions
     int hgroup[6];                     // hrec[hgroup[k] .. hgroup[k+1]) = terms with k directions
+    // grouped hierarchical kernel (H2, sgm_hier_host.cpp): group headers, parent paths, 8-byte
+    // step records and the kernel's own value layout; null when the set cannot be grouped
+    const int4* h2_groups;             // 3 x int4 per group
+    const int4* h2_parents;            // 2 x int4 per group
+    const int* h2_steps;               // 2 ints per step
+    const int* h2_maps;                // value slot of the H2 layout -> row of f (-1: padding)
+    int h2_n_groups, h2_n_vals;
+    int h2_root_off;                   // slot of the root's surplus in the H2 value table (-1: none)
     unsigned* flags;
     // segmented plans (sgm_eval_segments): segment of every term (consecutive, ascending) and
     // the distance in doubles between the outputs of consecutive segments; null otherwise
@@ -889,6 +897,161 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel H2: grouped hierarchical-surplus kernel (scalar output), the contract path of
+// method="auto".  Block = 32 points x W warps, bracket tables (hat value phi_e and new-knot
+// rank j_e per entry and point) in shared memory as in H1.  The multi-indices are walked as
+// GROUPS of up to 7 trie nodes with a common parent (tables and value layout:
+// sgm_hier_host.cpp): a group computes its members' weight / offset prefixes once
+// (w_g = w_par * phi, off_g = off_par + S_par * j) and then sweeps the entries of its largest
+// child set: ONE read of (phi_e, j_e) and one 8-byte record per step feed nv independent gathers
+//     acc_g += alpha[sbase + g * slot + off_g + S_mem * j_e] * phi_e,     g < nv.
+// L1 data-pipe cost per gather: the 8-byte surplus (one 128-byte line per warp: slots are
+// aligned) plus 1/nv of the bracket-table and record reads.  H1 paid 3 table wavefronts and
+// two 16-byte record loads per gather -- and a warp-wide load of UNIFORM data costs the pipe
+// 32 x its size, which is why the records here are 8 bytes per step and nothing per gather.
+// The warps of a block take groups from a shared counter (listed by decreasing cost), so the
+// end-of-tile barrier waits for at most one small group.
+// The order of the sum is not the reference's: this form makes no bit-exactness claim
+// (DESIGN.md 5.1), it is proven <= 1e-12 against the reference.
+// ---------------------------------------------------------------------------------------
+// steps [s0, s1) of a group, all with exactly NV members present: NV independent gathers per
+// step, issued before the first use (a warp issues in order: a load followed by its own FMA
+// would expose the full L1/L2 latency once per gather)
+template <int NV>
+__device__ __forceinline__ void hier_sweep(const int2* __restrict__ st, int s0, int s1,
+                                           const unsigned char* ybase, const unsigned char* ibase,
+                                           const double* __restrict__ A, int S_mem,
+                                           const int (&og)[7], double (&acc)[7]) {
+#pragma unroll 2
+    for (int s = s0; s < s1; ++s) {
+        const int2 r = __ldg(st + s);                // sbase, entry | nv << 12 | slot << 15
+        const unsigned ent = (unsigned)r.y & 0xfffu;
+        const int slot = (int)((unsigned)r.y >> 15);
+        const double phi = *reinterpret_cast<const double*>(ybase + 256u * ent);
+        const int ix = (int)*reinterpret_cast<const unsigned short*>(ibase + 64u * ent);
+        const double* a0 = A + (r.x + S_mem * ix);
+        double v[NV];
+#pragma unroll
+        for (int g = 0; g < NV; ++g) v[g] = __ldg(a0 + (g * slot + og[g]));
+#pragma unroll
+        for (int g = 0; g < NV; ++g) acc[g] = fma(v[g], phi, acc[g]);
+    }
+}
+
+template <int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB)
+eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                        const double* __restrict__ A, double* __restrict__ out, int64_t ldo,
+                        double scale, int accumulate, const int* __restrict__ perm) {
+    constexpr int KIND = SGM_HIER_PW_LINEAR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+    }
+    double* bas_all = sknots + 2 * (size_t)pl.n_knots;
+    double* sPart = bas_all + (size_t)pl.B * 32;              // [W][32]
+    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sPart + (size_t)W * 32);
+    int* sCounter = reinterpret_cast<int*>(idx_all + (size_t)pl.E * 32);
+    const unsigned char* ybase = reinterpret_cast<const unsigned char*>(bas_all + lane);
+    const unsigned char* ibase = reinterpret_cast<const unsigned char*>(idx_all + lane);
+#define SGM_HY(e) (*reinterpret_cast<const double*>(ybase + 256u * (unsigned)(e)))
+#define SGM_HI(e) ((int)*reinterpret_cast<const unsigned short*>(ibase + 64u * (unsigned)(e)))
+#define SGM_U16(v, j) (((unsigned)((j) < 2 ? (v).x : (j) < 4 ? (v).y : (j) < 6 ? (v).z : (v).w) >> (16 * ((j) & 1))) & 0xffffu)
+    const int n_groups = pl.h2_n_groups;
+    const int2* all_steps = reinterpret_cast<const int2*>(pl.h2_steps);
+
+    const int64_t n_tiles = (P + 31) >> 5;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t slot_p = (tile << 5) + lane;
+        const bool valid = slot_p < P;
+        const int64_t p = perm ? (int64_t)perm[valid ? slot_p : P - 1] : (valid ? slot_p : P - 1);
+        const double* xp = x + p * ldx;
+        __syncthreads();
+        for (int e = warp; e < pl.E; e += W) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
+                                             idx_all + lane, e, 32, pl.flags);
+        }
+        if (threadIdx.x == 0) *sCounter = 0;
+        __syncthreads();
+        double total = (warp == 0 && pl.h2_root_off >= 0) ? __ldg(A + pl.h2_root_off) : 0.0;
+#pragma unroll 1
+        for (;;) {
+            int gi = 0;
+            if (lane == 0) gi = atomicAdd(sCounter, 1);
+            gi = __shfl_sync(0xffffffffu, gi, 0);
+            if (gi >= n_groups) break;
+            const int4 h0 = __ldg(pl.h2_groups + 3 * (size_t)gi);      // first step, counts, S_par, S_mem
+            const int4 h1 = __ldg(pl.h2_groups + 3 * (size_t)gi + 1);  // member entries
+            const int4 h2 = __ldg(pl.h2_groups + 3 * (size_t)gi + 2);  // step bounds per member count
+            const int n_steps = h0.y & 0xffff, n_mem = (h0.y >> 16) & 0xf, n_par = (h0.y >> 20) & 0xf;
+            double w_par = 1.0;
+            int off_par = 0;
+            if (n_par) {                                               // warp-uniform
+                const int4 p0 = __ldg(pl.h2_parents + 2 * (size_t)gi);      // parent entries
+                const int4 p1 = __ldg(pl.h2_parents + 2 * (size_t)gi + 1);  // their extents
+                int stride = 1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < n_par) {
+                        const unsigned e = SGM_U16(p0, j);
+                        w_par = w_par * SGM_HY(e);
+                        off_par += SGM_HI(e) * stride;
+                        stride *= (int)SGM_U16(p1, j);
+                    }
+                }
+            }
+            double wg[7], acc[7];
+            int og[7];
+#pragma unroll
+            for (int g = 0; g < 7; ++g) {
+                const unsigned e = SGM_U16(h1, g);
+                acc[g] = 0.0;
+                wg[g] = w_par;                       // 0xffff: the parent itself (root) / unused slot
+                og[g] = off_par;
+                if (e != 0xffffu) {
+                    wg[g] = w_par * SGM_HY(e);
+                    og[g] = off_par + h0.z * SGM_HI(e);
+                }
+            }
+            // steps are listed by decreasing number of present members; h2 = first step with
+            // fewer than 7, 6, ..., 1 members (relative, 8 x u16)
+            const int2* st = all_steps + h0.x;
+            const int S_mem = h0.w;
+            const int e7 = (int)SGM_U16(h2, 0), e6 = (int)SGM_U16(h2, 1), e5 = (int)SGM_U16(h2, 2),
+                      e4 = (int)SGM_U16(h2, 3), e3 = (int)SGM_U16(h2, 4), e2 = (int)SGM_U16(h2, 5);
+            hier_sweep<7>(st, 0, e7, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<6>(st, e7, e6, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<5>(st, e6, e5, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<4>(st, e5, e4, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<3>(st, e4, e3, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<2>(st, e3, e2, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<1>(st, e2, n_steps, ybase, ibase, A, S_mem, og, acc);
+#pragma unroll
+            for (int g = 0; g < 7; ++g)
+                if (g < n_mem) total = fma(wg[g], acc[g], total);
+        }
+        sPart[warp * 32 + lane] = total;
+        __syncthreads();
+        if (warp == 0 && valid) {
+            double o = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) o = o + sPart[ww * 32 + lane];
+            double* dst = out + p * ldo;
+            *dst = accumulate ? *dst + scale * o : scale * o;
+        }
+    }
+#undef SGM_HY
+#undef SGM_HI
+#undef SGM_U16
+}
+
+// ---------------------------------------------------------------------------------------
 // Locality sort of the evaluation points (counting sort on a <= 16-bit key).  Each point is
 // evaluated independently, so the order only changes which points share a warp: with equal
 // coarse brackets the 32 lanes of a gather hit 1-2 cache lines instead of 4-5.
@@ -967,7 +1130,8 @@ __global__ void pregather_kernel(const int* __restrict__ maps, int64_t n_vals,
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = i / NF, c = i - j * NF;
-        G[i] = f[(int64_t)maps[j] * ldf + c];
+        const int row = maps[j];                       // -1: padding slot of an aligned layout
+        G[i] = row >= 0 ? f[(int64_t)row * ldf + c] : 0.0;
     }
 }
 

@@ -55,7 +55,7 @@ class HierarchicalPlan:
             raise NotImplementedError("knots(1) must be 0")
         # new knots of every rank >= 1 and the checks the one-basis-per-level form needs
         self.rank_knots = knots
-        newrank, newpos = [None], [None]
+        newrank, newpos, up = [None], [None], [None]
         for r in range(1, len(ms)):
             g, gp = knots[r], knots[r - 1]
             if np.any(np.diff(g) <= 0):
@@ -74,7 +74,15 @@ class HierarchicalPlan:
             nr[is_new] = np.arange(is_new.sum(), dtype=np.int32)
             newrank.append(nr)
             newpos.append(np.flatnonzero(is_new))
+            up.append(pos)                       # knot i of rank r-1 = knot up[r][i] of rank r
         self._newrank, self._newpos = newrank, newpos
+        # position of every knot of every rank in the FINEST knot vector: an integer name of
+        # the knot that is the same on all levels (the families are nested)
+        R = len(ms) - 1
+        fin = [None] * (R + 1)
+        fin[R] = np.arange(knots[R].size, dtype=np.int64)
+        for r in range(R - 1, -1, -1):
+            fin[r] = fin[r + 1][up[r + 1]]
 
         # hierarchical nodes: term nu has one node per tuple of new knots (C order)
         n_fam = len(ms) - 1                                  # family f = rank f + 1
@@ -106,6 +114,34 @@ class HierarchicalPlan:
                 grids = np.indices(shape).reshape(act.size, -1)
                 for a, d in enumerate(act):
                     node_pos[lo:hi, d] = newpos[ranks[t, d]][grids[a]]
+        # integer key of a node: the finest-level positions of its coordinates, hashed with
+        # random odd multipliers (collisions are excluded by comparing the rows afterwards)
+        node_fin = np.empty((self.M, N), dtype=np.int64)
+        for r in range(R + 1):
+            sel_r = node_rank == r
+            node_fin[sel_r] = fin[r][node_pos[sel_r]]
+        mult = np.random.default_rng(0x5eed).integers(1, 2 ** 62, N, dtype=np.int64) * 2 + 1
+        with np.errstate(over="ignore"):
+            keys = (node_fin * mult).sum(axis=1)
+        order = np.argsort(keys, kind="stable")
+        skeys = keys[order]
+
+        def find(ch, d, fin_pos):
+            """Rows of the nodes that equal node ch except for knot `fin_pos` in direction d."""
+            with np.errstate(over="ignore"):
+                probe = keys[ch] + (fin_pos - node_fin[ch, d]) * mult[d]
+            at = np.clip(np.searchsorted(skeys, probe), 0, self.M - 1)
+            par = order[at]
+            ok = skeys[at] == probe
+            if ok.all():                                       # exact check of the hashed match
+                want = node_fin[ch].copy()
+                want[:, d] = fin_pos
+                ok = (node_fin[par] == want).all(axis=1)
+            if not ok.all():
+                raise NotImplementedError("a hierarchical parent node is missing (set not "
+                                          "downward closed?)")
+            return par
+
         # hierarchisation batches: for every direction, finest rank first
         self.batches = []
         for d in range(N):
@@ -125,9 +161,8 @@ class HierarchicalPlan:
                     ia, ib = old[k - 1], old[k]
                     tpar = (g[i] - g[ia]) / (g[ib] - g[ia])
                     wa, wb = 1.0 - tpar, tpar
-                pa = self._find_parents(nodes, ch, d, g[ia])
-                pb = self._find_parents(nodes, ch, d, g[ib]) if old.size > 1 else \
-                    np.full(ch.size, -1, dtype=np.int64)
+                pa = find(ch, d, fin[r][ia])
+                pb = find(ch, d, fin[r][ib]) if old.size > 1 else np.full(ch.size, -1, dtype=np.int64)
                 self.batches.append((ch.astype(np.int32), pa.astype(np.int32), pb.astype(np.int32),
                                      wa.astype(np.float64), wb.astype(np.float64)))
 
@@ -149,14 +184,6 @@ class HierarchicalPlan:
                 maps_f[lo:hi] = lo + np.arange(hi - lo, dtype=np.int32).reshape(shape).ravel(order="F")
         self._maps_f = maps_f
         self._device = {}
-
-    def _find_parents(self, nodes, ch, d, coord):
-        probe = nodes[ch].copy()
-        probe[:, d] = coord
-        par = _lib.match_rows(probe, nodes, NODE_TOL)
-        if np.any(par < 0):
-            raise NotImplementedError("a hierarchical parent node is missing (set not downward closed?)")
-        return par
 
     # ------------------------------------------------------------------------------ device
     def _dev(self, device):

@@ -38,8 +38,88 @@ def emulate(hp, x, f):
     return out
 
 
+def emulate_groups(hp, x, f):
+    """numpy twin of eval_hier_groups_kernel (kernel H2) on the tables of
+    sgm_host_hier_groups: same traversal, same operations."""
+    from sgmethods_b200 import _lib
+    alpha = np.array(f[hp.sel], dtype=float)
+    for ch, pa, pb, wa, wb in hp.batches:
+        coarse = wa[:, None] * alpha[pa]
+        two = pb >= 0
+        coarse[two] = coarse[two] + wb[two, None] * alpha[pb[two]]
+        alpha[ch] -= coarse
+    tf = hp._term_fam
+    T, N = tf.shape
+    n_fam = len(hp.rank_knots) - 1
+    extent = np.array([(hp._newrank[r] >= 0).sum() for r in range(1, n_fam + 1)], dtype=np.int32)
+    groups, parents, steps, hmap, root = _lib.hier_groups(tf, extent, hp._map_off[:T])
+    # the kernel's own value table: a gather of the surpluses through hmap, zeros in the padding
+    used = hmap[hmap >= 0]
+    assert np.array_equal(np.sort(used), np.arange(hp._map_off[T]))      # every surplus exactly once
+    A = np.where((hmap >= 0)[:, None], alpha[hp._maps_f[np.maximum(hmap, 0)]], 0.0)
+    # entries in order of first use (the plan's numbering) with their per-point tables
+    ent = {}
+    for t in range(T):
+        for d in range(N):
+            if tf[t, d] >= 0 and (d, tf[t, d]) not in ent:
+                ent[(d, tf[t, d])] = len(ent)
+    phi = np.zeros((len(ent), x.shape[0]))
+    rank = np.zeros((len(ent), x.shape[0]), dtype=np.int64)
+    for (d, fam), e in ent.items():
+        g, nr = hp.rank_knots[fam + 1], hp._newrank[fam + 1]
+        i = np.clip(np.searchsorted(g, x[:, d], side="right") - 1, 0, g.size - 2)
+        y = (x[:, d] - g[i]) / (g[i + 1] - g[i])
+        lo_new = nr[i] >= 0
+        phi[e] = np.where(lo_new, 1 - y, y)
+        rank[e] = np.where(lo_new, nr[i], nr[i + 1])
+    out = np.zeros((x.shape[0], f.shape[1])) + (A[root] if root >= 0 else 0.0)
+    leaves = 0
+    for gr, pr in zip(groups, parents):
+        n_steps, n_mem, n_par = gr[1] & 0xffff, (gr[1] >> 16) & 0xf, (gr[1] >> 20) & 0xf
+        pu, mu = pr.view(np.uint16), gr.view(np.uint16)
+        w_par, off_par, stride = np.ones(x.shape[0]), np.zeros(x.shape[0], dtype=np.int64), 1
+        for j in range(n_par):
+            w_par = w_par * phi[pu[j]]
+            off_par = off_par + rank[pu[j]] * stride
+            stride *= int(pu[8 + j])
+        assert stride == gr[2]
+        acc = [np.zeros_like(out) for _ in range(n_mem)]
+        w, off = [], []
+        for m in range(n_mem):
+            e = mu[8 + m]
+            w.append(w_par if e == 0xffff else w_par * phi[e])
+            off.append(off_par if e == 0xffff else off_par + gr[2] * rank[e])
+        bounds = gr.view(np.uint16)[16:24]
+        for si, (sbase, word) in enumerate(steps[gr[0]:gr[0] + n_steps]):
+            e, nv, slot = word & 0xfff, (word >> 12) & 7, (int(word) & 0xffffffff) >> 15
+            assert 1 <= nv <= n_mem
+            assert all((si < bounds[i]) == (nv >= 7 - i) for i in range(7))   # sorted by nv
+            for m in range(nv):
+                idx = sbase + m * slot + off[m] + gr[3] * rank[e]
+                assert (idx // 16 == (sbase + m * slot) // 16).all() or slot > 16   # one 128-byte line
+                acc[m] += A[idx] * phi[e][:, None]
+                leaves += 1
+        for m in range(n_mem):
+            out += w[m][:, None] * acc[m]
+    assert leaves == T - (1 if root >= 0 else 0)            # every non-root multi-index exactly once
+    return out
+
+
+@pytest.mark.parametrize("case", ["cc", "gauss", "aniso"])
+def test_group_tables_of_the_grouped_kernel_reproduce_the_combination_formula(case):
+    it, hp, x, f, ref = _case(case)
+    got = emulate_groups(hp, x, f)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("case", ["cc", "gauss", "aniso"])
 def test_hierarchical_tables_reproduce_the_combination_formula(case):
+    it, hp, x, f, ref = _case(case)
+    got = emulate(hp, x, f)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def _case(case):
     rng = np.random.default_rng(3)
     if case == "cc":
         S, knots = mis.smolyak_mid_set(4, 3), nodes_1d.cc_nodes
@@ -59,8 +139,7 @@ def test_hierarchical_tables_reproduce_the_combination_formula(case):
     ref = sg_oracle.interpolate(
         sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
                                    it.active_tp_nodes_list, it.map_tp_to_SG), x, f, squeeze=False)
-    got = emulate(hp, x, f)
-    assert np.max(np.abs(got - ref)) <= 1e-11 * np.max(np.abs(ref))
+    return it, hp, x, f, ref
 
 
 def test_hierarchical_form_rejects_what_it_cannot_represent():
