@@ -75,7 +75,7 @@ struct Knobs {
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
         if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
         if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
-        if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 3;
+        if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 6;
         return k;
     }
 };
@@ -381,14 +381,18 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
     if (KIND == SGM_HIER_PW_LINEAR && use_h2_kernel(plan)) {
         // launch shapes of the grouped kernel, best first (dev knob SGM_H2_SHAPE picks one)
         struct Shape { SplitKernel kern; int warps; };
-        const Shape shapes[3] = {{sgm::eval_hier_groups_kernel<16, 2>, 16},
-                                 {sgm::eval_hier_groups_kernel<8, 3>, 8},
-                                 {sgm::eval_hier_groups_kernel<16, 1>, 16}};
+        constexpr int NS = 6;
+        const Shape shapes[NS] = {{sgm::eval_hier_groups_kernel<16, 2, 2, false>, 16},
+                                  {sgm::eval_hier_groups_kernel<14, 2, 2, false>, 14},
+                                  {sgm::eval_hier_groups_kernel<12, 2, 2, false>, 12},
+                                  {sgm::eval_hier_groups_kernel<8, 3, 2, false>, 8},
+                                  {sgm::eval_hier_groups_kernel<16, 1, 2, false>, 16},
+                                  {sgm::eval_hier_groups_kernel<12, 2, 4, false>, 12}};
         const PlanDev& d = plan->dev;
-        for (int si = 0; si < 3; ++si) {
-            const Shape& sh = shapes[(si + plan->knobs.h2_shape) % 3];
-            const size_t smem = (size_t)d.n_knots * 16 + (size_t)d.B * 32 * 8 + (size_t)sh.warps * 32 * 8 +
-                                (size_t)d.E * 32 * 2 + 64 + 16;
+        for (int si = 0; si < NS; ++si) {
+            const Shape& sh = shapes[(si + plan->knobs.h2_shape) % NS];
+            const size_t smem = (size_t)d.n_knots * 16 + (size_t)(d.B + 1) * 32 * 8 + (size_t)sh.warps * 32 * 8 +
+                                (size_t)(d.E + 1) * 32 * 2 + 64 + 16;
             if (smem > (size_t)plan->max_smem_optin ||
                 cudaFuncSetAttribute(sh.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 continue;
@@ -1151,7 +1155,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     }
     d.flags = const_cast<unsigned*>(cflags);
     d.h2_groups = reinterpret_cast<const int4*>(h2g);
-    d.h2_parents = reinterpret_cast<const int4*>(h2p);
+    d.h2_parents = h2p;
     d.h2_n_groups = (int)(h2_groups.size() / 12);
     d.h2_n_vals = (int)h2_maps.size();
     d.h2_root_off = h2_root;

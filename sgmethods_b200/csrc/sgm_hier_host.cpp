@@ -23,11 +23,13 @@
 // 128-byte line.  Nothing per (step, member) is stored.  Tables (all int32):
 //   group (12 ints): [0] first step, [1] steps | n_mem << 16 | n_par << 20, [2] S_par (size of
 //                    the parent's block), [3] S_mem (size of a member's block = stride of the
-//                    leaf direction), [4..7] member entries (8 x u16, 0xffff: the parent itself
-//                    -- the root group), [8..11] 8 x u16: the steps are listed by decreasing nv,
-//                    entry i = first step (relative) with fewer than 7 - i members present;
-//   parent (8 ints): [0..3] parent entries (8 x u16), [4..7] their extents (8 x u16);
-//   step (2 ints):   [0] sbase, [1] entry | nv << 12 | slot << 15.
+//                    leaf direction), [4..7] member entries * 64 (8 x u16; unused slots and the
+//                    root group's "member = the parent itself" name the DUMMY entry n_entries,
+//                    whose hat value is 1 and rank 0), [8..11] 8 x u16: the steps are listed by
+//                    decreasing nv (then by slot size), entry i = first step (relative) with
+//                    fewer than 7 - i members present;
+//   parent (8 ints): word j = entry_j * 64 | extent_j << 16 along the parent's path;
+//   step (2 ints):   [0] sbase, [1] entry * 64 | slot << 16.
 // Groups are listed by decreasing cost: the kernel's warps take them from a shared counter.
 #include <algorithm>
 #include <cstdint>
@@ -40,8 +42,8 @@
 namespace {
 constexpr int kMaxMembers = 7;
 constexpr int kMaxParent = 8;
-constexpr int kMaxEntries = 4095;           // 12 bits in a step record
-constexpr int64_t kMaxSlot = (1 << 17) - 1; // 17 bits in a step record
+constexpr int kMaxEntries = 1022;           // entry * 64 (and the dummy entry) in 16 bits
+constexpr int64_t kMaxSlot = 0xffff;        // 16 bits in a step record
 
 struct Group {
     int g[12];
@@ -118,42 +120,41 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
         std::memset(G.par, 0, sizeof G.par);
         const int n_par = parent >= 0 ? (int)path[parent].size() : 0;
         int64_t S_par = 1;
-        unsigned short* pe = reinterpret_cast<unsigned short*>(G.par);
+        const int dummy64 = (int)ent_fam.size() * 64;
         for (int j = 0; j < n_par; ++j) {
             const int e = path[parent][j];
             if (extent(e) > 0xffff) { ok = false; return; }
-            pe[j] = (unsigned short)e;
-            pe[8 + j] = (unsigned short)extent(e);
+            G.par[j] = (e * 64) | ((int)extent(e) << 16);
             S_par *= extent(e);
             if (S_par > 0x3fffffff) { ok = false; return; }
         }
         unsigned short* me = reinterpret_cast<unsigned short*>(G.g + 4);
-        for (int j = 0; j < 8; ++j) me[j] = 0xffff;
+        for (int j = 0; j < 8; ++j) me[j] = (unsigned short)dummy64;
         int64_t S_mem = S_par;
         if (parent >= 0) {
-            for (size_t m = 0; m < members.size(); ++m) me[m] = (unsigned short)path[members[m]].back();
+            for (size_t m = 0; m < members.size(); ++m) me[m] = (unsigned short)(path[members[m]].back() * 64);
             S_mem = S_par * extent(path[members[0]].back());
             if (S_mem > 0x3fffffff) { ok = false; return; }
         }
         int64_t leaves = 0;
         // the sweep: entries of the largest set, by decreasing number of members that have them
-        std::vector<std::pair<int, int>> sweep;                // (-nv, entry)
+        std::vector<std::pair<std::pair<int, int64_t>, int>> sweep;   // ((-nv, extent), entry)
         for (const auto& kv : kids[members[0]]) {
             int nv = 0;
             while (nv < (int)members.size() && kids[members[nv]].count(kv.first)) ++nv;
-            sweep.push_back({-nv, kv.first});
+            sweep.push_back({{-nv, extent(kv.first)}, kv.first});
         }
         std::sort(sweep.begin(), sweep.end());
         if (sweep.size() > 0xffff) { ok = false; return; }
         unsigned short* bounds = reinterpret_cast<unsigned short*>(G.g + 8);
         for (int i = 0; i < 8; ++i) {                          // first step with nv < 7 - i
             size_t sidx = 0;
-            while (sidx < sweep.size() && -sweep[sidx].first >= 7 - i) ++sidx;
+            while (sidx < sweep.size() && -sweep[sidx].first.first >= 7 - i) ++sidx;
             bounds[i] = (unsigned short)sidx;
         }
         for (const auto& sw : sweep) {
             const int e = sw.second;
-            const int nv = -sw.first;
+            const int nv = -sw.first.first;
             const int64_t need = S_mem * extent(e);
             int64_t slot = need;
             if (need <= 16) { slot = 1; while (slot < need) slot <<= 1; }
@@ -162,7 +163,7 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
             const int64_t align = std::min<int64_t>(slot, 16);
             G.vals = (G.vals + align - 1) / align * align;
             G.step_words.push_back((int)G.vals);
-            G.step_words.push_back(e | (nv << 12) | ((int)slot << 15));
+            G.step_words.push_back((e * 64) | (int)((unsigned)slot << 16));
             for (int g = 0; g < nv; ++g)
                 G.blocks.push_back({G.vals + g * slot, {kids[members[g]].at(e), need}});
             G.vals += nv * slot;

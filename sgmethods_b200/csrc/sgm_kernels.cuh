@@ -75,7 +75,7 @@ struct PlanDev {
     // grouped hierarchical kernel (H2, sgm_hier_host.cpp): group headers, parent paths, 8-byte
     // step records and the kernel's own value layout; null when the set cannot be grouped
     const int4* h2_groups;             // 3 x int4 per group
-    const int4* h2_parents;            // 2 x int4 per group
+    const int* h2_parents;             // 8 ints per group
     const int* h2_steps;               // 2 ints per step
     const int* h2_maps;                // value slot of the H2 layout -> row of f (-1: padding)
     int h2_n_groups, h2_n_vals;
@@ -914,31 +914,60 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 // The order of the sum is not the reference's: this form makes no bit-exactness claim
 // (DESIGN.md 5.1), it is proven <= 1e-12 against the reference.
 // ---------------------------------------------------------------------------------------
+// Table loads of the grouped kernel: read-only path, kept in L1 in preference to the surplus
+// lines (the 0.5 MB value table streams through L1 once per tile and would evict them).
+__device__ __forceinline__ int2 ldg_keep(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ldg_keep(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_keep(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // steps [s0, s1) of a group, all with exactly NV members present: NV independent gathers per
 // step, issued before the first use (a warp issues in order: a load followed by its own FMA
-// would expose the full L1/L2 latency once per gather)
-template <int NV>
+// would expose the full L1/L2 latency once per gather).  Address of member g's surplus:
+// A + 8 (sbase + S_mem j_e) + 8 (g slot + off_g): two integer multiply-adds, the load and the
+// FMA per gather; no branch inside the loop, the next step's record is fetched a step ahead.
+template <int NV, int UNROLL>
 __device__ __forceinline__ void hier_sweep(const int2* __restrict__ st, int s0, int s1,
                                            const unsigned char* ybase, const unsigned char* ibase,
                                            const double* __restrict__ A, int S_mem,
                                            const int (&og)[7], double (&acc)[7]) {
-#pragma unroll 2
+    if (s0 >= s1) return;
+    int2 r = ldg_keep(st + s0);                      // sbase, entry * 64 | slot << 16
+#pragma unroll UNROLL
     for (int s = s0; s < s1; ++s) {
-        const int2 r = __ldg(st + s);                // sbase, entry | nv << 12 | slot << 15
-        const unsigned ent = (unsigned)r.y & 0xfffu;
-        const int slot = (int)((unsigned)r.y >> 15);
-        const double phi = *reinterpret_cast<const double*>(ybase + 256u * ent);
-        const int ix = (int)*reinterpret_cast<const unsigned short*>(ibase + 64u * ent);
-        const double* a0 = A + (r.x + S_mem * ix);
+        const int2 rn = ldg_keep(st + min(s + 1, s1 - 1));   // next record: off the dependency chain
+        const unsigned e64 = (unsigned)r.y & 0xffffu;
+        const unsigned slot = (unsigned)r.y >> 16;
+        const double phi = *reinterpret_cast<const double*>(ybase + 4u * e64);
+        const unsigned ix = *reinterpret_cast<const unsigned short*>(ibase + e64);
+        const double* a0 = A + (unsigned)(r.x + S_mem * (int)ix);
         double v[NV];
 #pragma unroll
-        for (int g = 0; g < NV; ++g) v[g] = __ldg(a0 + (g * slot + og[g]));
+        for (int g = 0; g < NV; ++g) {               // address = a0 + 8 * u32: one mad.wide.u32
+            const unsigned u = (unsigned)g * slot + (unsigned)og[g];
+            unsigned long long addr;
+            asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(u), "l"(a0));
+            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v[g]) : "l"(addr));
+        }
 #pragma unroll
         for (int g = 0; g < NV; ++g) acc[g] = fma(v[g], phi, acc[g]);
+        r = rn;
     }
 }
 
-template <int W, int MINB>
+template <int W, int MINB, int UNROLL, bool CONTIG>
 __global__ void __launch_bounds__(W * 32, MINB)
 eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
                         const double* __restrict__ A, double* __restrict__ out, int64_t ldo,
@@ -953,20 +982,27 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
         sknots[i] = pl.knots[i];
         reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
     }
+    // bracket tables [E + 1][32]: row E is the DUMMY entry (hat value 1, rank 0) that unused
+    // member slots and the root group point to, so the member set-up needs no predicates
     double* bas_all = sknots + 2 * (size_t)pl.n_knots;
-    double* sPart = bas_all + (size_t)pl.B * 32;              // [W][32]
+    double* sPart = bas_all + (size_t)(pl.B + 1) * 32;        // [W][32]
     unsigned short* idx_all = reinterpret_cast<unsigned short*>(sPart + (size_t)W * 32);
-    int* sCounter = reinterpret_cast<int*>(idx_all + (size_t)pl.E * 32);
+    int* sCounter = reinterpret_cast<int*>(idx_all + (size_t)(pl.E + 1) * 32);
+    if (threadIdx.x < 32) {
+        bas_all[(size_t)pl.B * 32 + threadIdx.x] = 1.0;
+        idx_all[(size_t)pl.E * 32 + threadIdx.x] = 0;
+    }
     const unsigned char* ybase = reinterpret_cast<const unsigned char*>(bas_all + lane);
     const unsigned char* ibase = reinterpret_cast<const unsigned char*>(idx_all + lane);
-#define SGM_HY(e) (*reinterpret_cast<const double*>(ybase + 256u * (unsigned)(e)))
-#define SGM_HI(e) ((int)*reinterpret_cast<const unsigned short*>(ibase + 64u * (unsigned)(e)))
-#define SGM_U16(v, j) (((unsigned)((j) < 2 ? (v).x : (j) < 4 ? (v).y : (j) < 6 ? (v).z : (v).w) >> (16 * ((j) & 1))) & 0xffffu)
     const int n_groups = pl.h2_n_groups;
     const int2* all_steps = reinterpret_cast<const int2*>(pl.h2_steps);
 
     const int64_t n_tiles = (P + 31) >> 5;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // CONTIG: a block takes a contiguous range of tiles (neighbours in the locality order)
+    const int64_t tile_begin = CONTIG ? n_tiles * blockIdx.x / gridDim.x : blockIdx.x;
+    const int64_t tile_end = CONTIG ? n_tiles * (blockIdx.x + 1) / gridDim.x : n_tiles;
+    const int64_t tile_step = CONTIG ? 1 : gridDim.x;
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int64_t slot_p = (tile << 5) + lane;
         const bool valid = slot_p < P;
         const int64_t p = perm ? (int64_t)perm[valid ? slot_p : P - 1] : (valid ? slot_p : P - 1);
@@ -986,55 +1022,56 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             if (lane == 0) gi = atomicAdd(sCounter, 1);
             gi = __shfl_sync(0xffffffffu, gi, 0);
             if (gi >= n_groups) break;
-            const int4 h0 = __ldg(pl.h2_groups + 3 * (size_t)gi);      // first step, counts, S_par, S_mem
-            const int4 h1 = __ldg(pl.h2_groups + 3 * (size_t)gi + 1);  // member entries
-            const int4 h2 = __ldg(pl.h2_groups + 3 * (size_t)gi + 2);  // step bounds per member count
-            const int n_steps = h0.y & 0xffff, n_mem = (h0.y >> 16) & 0xf, n_par = (h0.y >> 20) & 0xf;
+            const int4* gh = pl.h2_groups + 3 * (size_t)gi;
+            const int4 h0 = ldg_keep(gh);    // first step, steps | n_mem << 16 | n_par << 20, S_par, S_mem
+            const int4 h1 = ldg_keep(gh + 1);// member entries * 64 (8 x u16; unused: the dummy entry)
+            const int4 h2 = ldg_keep(gh + 2);// step bounds per member count (8 x u16)
+            const int n_steps = h0.y & 0xffff, n_par = (h0.y >> 20) & 0xf;
             double w_par = 1.0;
             int off_par = 0;
-            if (n_par) {                                               // warp-uniform
-                const int4 p0 = __ldg(pl.h2_parents + 2 * (size_t)gi);      // parent entries
-                const int4 p1 = __ldg(pl.h2_parents + 2 * (size_t)gi + 1);  // their extents
+            {                                // the parent's path: entry * 64 | extent << 16 per word
+                const int* pw = pl.h2_parents + 8 * (size_t)gi;
                 int stride = 1;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < n_par) {
-                        const unsigned e = SGM_U16(p0, j);
-                        w_par = w_par * SGM_HY(e);
-                        off_par += SGM_HI(e) * stride;
-                        stride *= (int)SGM_U16(p1, j);
-                    }
+#pragma unroll 1
+                for (int j = 0; j < n_par; ++j) {
+                    const unsigned w = (unsigned)ldg_keep(pw + j);
+                    const unsigned e64 = w & 0xffffu;
+                    w_par = w_par * *reinterpret_cast<const double*>(ybase + 4u * e64);
+                    off_par += (int)*reinterpret_cast<const unsigned short*>(ibase + e64) * stride;
+                    stride *= (int)(w >> 16);
                 }
             }
-            double wg[7], acc[7];
+            double acc[7];
             int og[7];
+            const unsigned me[4] = {(unsigned)h1.x, (unsigned)h1.y, (unsigned)h1.z, (unsigned)h1.w};
 #pragma unroll
             for (int g = 0; g < 7; ++g) {
-                const unsigned e = SGM_U16(h1, g);
+                const unsigned e64 = (g & 1) ? me[g >> 1] >> 16 : me[g >> 1] & 0xffffu;
                 acc[g] = 0.0;
-                wg[g] = w_par;                       // 0xffff: the parent itself (root) / unused slot
-                og[g] = off_par;
-                if (e != 0xffffu) {
-                    wg[g] = w_par * SGM_HY(e);
-                    og[g] = off_par + h0.z * SGM_HI(e);
-                }
+                og[g] = off_par + h0.z * (int)*reinterpret_cast<const unsigned short*>(ibase + e64);
             }
-            // steps are listed by decreasing number of present members; h2 = first step with
-            // fewer than 7, 6, ..., 1 members (relative, 8 x u16)
+            // steps are listed by decreasing number of present members; bound i = first step
+            // (relative) with fewer than 7 - i members
             const int2* st = all_steps + h0.x;
             const int S_mem = h0.w;
-            const int e7 = (int)SGM_U16(h2, 0), e6 = (int)SGM_U16(h2, 1), e5 = (int)SGM_U16(h2, 2),
-                      e4 = (int)SGM_U16(h2, 3), e3 = (int)SGM_U16(h2, 4), e2 = (int)SGM_U16(h2, 5);
-            hier_sweep<7>(st, 0, e7, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<6>(st, e7, e6, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<5>(st, e6, e5, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<4>(st, e5, e4, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<3>(st, e4, e3, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<2>(st, e3, e2, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<1>(st, e2, n_steps, ybase, ibase, A, S_mem, og, acc);
+            const int e7 = h2.x & 0xffff, e6 = (unsigned)h2.x >> 16, e5 = h2.y & 0xffff,
+                      e4 = (unsigned)h2.y >> 16, e3 = h2.z & 0xffff, e2 = (unsigned)h2.z >> 16;
+            hier_sweep<7, UNROLL>(st, 0, e7, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<6, UNROLL>(st, e7, e6, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<5, UNROLL>(st, e6, e5, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<4, UNROLL>(st, e5, e4, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<3, UNROLL>(st, e4, e3, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<2, UNROLL>(st, e3, e2, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<1, UNROLL>(st, e2, n_steps, ybase, ibase, A, S_mem, og, acc);
+            // total += w_par * sum_g phi(e_g) acc_g; the members' hat values are read again here
+            // instead of living in 14 registers during the sweeps (unused slots: acc = 0)
+            double gsum = 0.0;
 #pragma unroll
-            for (int g = 0; g < 7; ++g)
-                if (g < n_mem) total = fma(wg[g], acc[g], total);
+            for (int g = 0; g < 7; ++g) {
+                const unsigned e64 = (g & 1) ? me[g >> 1] >> 16 : me[g >> 1] & 0xffffu;
+                gsum = fma(*reinterpret_cast<const double*>(ybase + 4u * e64), acc[g], gsum);
+            }
+            total = fma(w_par, gsum, total);
         }
         sPart[warp * 32 + lane] = total;
         __syncthreads();
@@ -1046,9 +1083,6 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             *dst = accumulate ? *dst + scale * o : scale * o;
         }
     }
-#undef SGM_HY
-#undef SGM_HI
-#undef SGM_U16
 }
 
 // ---------------------------------------------------------------------------------------

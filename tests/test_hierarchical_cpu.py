@@ -76,24 +76,27 @@ def emulate_groups(hp, x, f):
     leaves = 0
     for gr, pr in zip(groups, parents):
         n_steps, n_mem, n_par = gr[1] & 0xffff, (gr[1] >> 16) & 0xf, (gr[1] >> 20) & 0xf
-        pu, mu = pr.view(np.uint16), gr.view(np.uint16)
+        mu = gr.view(np.uint16)
         w_par, off_par, stride = np.ones(x.shape[0]), np.zeros(x.shape[0], dtype=np.int64), 1
         for j in range(n_par):
-            w_par = w_par * phi[pu[j]]
-            off_par = off_par + rank[pu[j]] * stride
-            stride *= int(pu[8 + j])
+            e, ext = (int(pr[j]) & 0xffff) // 64, (int(pr[j]) & 0xffffffff) >> 16
+            w_par = w_par * phi[e]
+            off_par = off_par + rank[e] * stride
+            stride *= ext
         assert stride == gr[2]
         acc = [np.zeros_like(out) for _ in range(n_mem)]
         w, off = [], []
-        for m in range(n_mem):
-            e = mu[8 + m]
-            w.append(w_par if e == 0xffff else w_par * phi[e])
-            off.append(off_par if e == 0xffff else off_par + gr[2] * rank[e])
-        bounds = gr.view(np.uint16)[16:24]
+        for m in range(7):
+            e = int(mu[8 + m]) // 64             # the dummy entry (hat 1, rank 0) where unused
+            assert int(mu[8 + m]) % 64 == 0 and (e < len(ent) or (e == len(ent) and (m >= n_mem or n_par == 0)))
+            if m < n_mem:
+                w.append(w_par * (phi[e] if e < len(ent) else 1.0))
+                off.append(off_par + gr[2] * (rank[e] if e < len(ent) else 0))
+        bounds = [int(b) for b in gr.view(np.uint16)[16:24]]
         for si, (sbase, word) in enumerate(steps[gr[0]:gr[0] + n_steps]):
-            e, nv, slot = word & 0xfff, (word >> 12) & 7, (int(word) & 0xffffffff) >> 15
+            e, slot = (int(word) & 0xffff) // 64, (int(word) & 0xffffffff) >> 16
+            nv = 7 - next(i for i in range(8) if si < bounds[i] or i == 7)      # member count class
             assert 1 <= nv <= n_mem
-            assert all((si < bounds[i]) == (nv >= 7 - i) for i in range(7))   # sorted by nv
             for m in range(nv):
                 idx = sbase + m * slot + off[m] + gr[3] * rank[e]
                 assert (idx // 16 == (sbase + m * slot) // 16).all() or slot > 16   # one 128-byte line

@@ -42,9 +42,10 @@ def timed(label):
 os.environ["SGM_NO_H2"] = "1"
 timed("H1 (per multi-index)")
 del os.environ["SGM_NO_H2"]
-for shape, label in ((0, "H2 16 warps x2 (64 regs)"), (1, "H2 8 warps x3 (80 regs)"), (2, "H2 16 warps x1 (104 regs)")):
+for shape, label in ((0, "16w x2 (64 regs)"), (1, "14w x2 (73 regs)"), (2, "12w x2 (85 regs)"),
+                     (3, "8w x3 (85 regs)"), (4, "16w x1 (128 regs)"), (5, "12w x2 unroll4")):
     os.environ["SGM_H2_SHAPE"] = str(shape)
-    timed(label)
+    timed("H2 " + label)
 del os.environ["SGM_H2_SHAPE"]
 reload_knobs()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
