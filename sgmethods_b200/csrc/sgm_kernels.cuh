@@ -939,15 +939,16 @@ __device__ __forceinline__ int ldg_keep(const int* p) {
 // A + 8 (sbase + S_mem j_e) + 8 (g slot + off_g): two integer multiply-adds, the load and the
 // FMA per gather; no branch inside the loop, the next step's record is fetched a step ahead.
 template <int NV, int UNROLL>
-__device__ __forceinline__ void hier_sweep(const int2* __restrict__ st, int s0, int s1,
-                                           const unsigned char* ybase, const unsigned char* ibase,
+__device__ __forceinline__ void hier_sweep(const int2* __restrict__ st, int s0, int s1, int s_last,
+                                           int2& r, const unsigned char* ybase,
+                                           const unsigned char* ibase,
                                            const double* __restrict__ A, int S_mem,
                                            const int (&og)[7], double (&acc)[7]) {
-    if (s0 >= s1) return;
-    int2 r = ldg_keep(st + s0);                      // sbase, entry * 64 | slot << 16
+    // r = record of step s0 (sbase, entry * 64 | slot << 16), fetched by the caller / the
+    // previous sweep of the group; on return the record of step s1
 #pragma unroll UNROLL
     for (int s = s0; s < s1; ++s) {
-        const int2 rn = ldg_keep(st + min(s + 1, s1 - 1));   // next record: off the dependency chain
+        const int2 rn = ldg_keep(st + min(s + 1, s_last));   // next record: off the dependency chain
         const unsigned e64 = (unsigned)r.y & 0xffffu;
         const unsigned slot = (unsigned)r.y >> 16;
         const double phi = *reinterpret_cast<const double*>(ybase + 4u * e64);
@@ -1056,13 +1057,14 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             const int S_mem = h0.w;
             const int e7 = h2.x & 0xffff, e6 = (unsigned)h2.x >> 16, e5 = h2.y & 0xffff,
                       e4 = (unsigned)h2.y >> 16, e3 = h2.z & 0xffff, e2 = (unsigned)h2.z >> 16;
-            hier_sweep<7, UNROLL>(st, 0, e7, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<6, UNROLL>(st, e7, e6, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<5, UNROLL>(st, e6, e5, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<4, UNROLL>(st, e5, e4, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<3, UNROLL>(st, e4, e3, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<2, UNROLL>(st, e3, e2, ybase, ibase, A, S_mem, og, acc);
-            hier_sweep<1, UNROLL>(st, e2, n_steps, ybase, ibase, A, S_mem, og, acc);
+            int2 r = ldg_keep(st);
+            hier_sweep<7, UNROLL>(st, 0, e7, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<6, UNROLL>(st, e7, e6, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<5, UNROLL>(st, e6, e5, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<4, UNROLL>(st, e5, e4, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<3, UNROLL>(st, e4, e3, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<2, UNROLL>(st, e3, e2, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
+            hier_sweep<1, UNROLL>(st, e2, n_steps, n_steps - 1, r, ybase, ibase, A, S_mem, og, acc);
             // total += w_par * sum_g phi(e_g) acc_g; the members' hat values are read again here
             // instead of living in 14 registers during the sweeps (unused slots: acc = 0)
             double gsum = 0.0;
