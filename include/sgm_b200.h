@@ -109,12 +109,15 @@ void sgm_grid_destroy(sgm_grid* g);
  *   family), val_off T (offset of every term's surplus block, first direction fastest).
  * Call with groups = parents = steps = hmap = NULL to get the sizes: groups 12 and parents 8 ints
  * per group, steps 2 ints each, hmap n_slots ints (value slot of the kernel's layout -> index
- * in the caller's layout, -1 = padding); root_slot = slot of the zero multi-index.
+ * in the caller's layout, -1 = padding); root_slot = slot of the zero multi-index; split
+ * n_lists + 1 ints: the groups are dealt to n_lists lists of near-equal cost, list w = groups
+ * [split[w], split[w+1]) (one list per warp of the kernel: a fixed summation order).
  * SGM_ERR_INVALID if the set is not downward closed. */
 int sgm_host_hier_groups(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
                          const int32_t* fam_extent, const int64_t* val_off,
-                         int64_t* n_groups, int64_t* n_steps, int64_t* n_slots, int32_t* root_slot,
-                         int32_t* groups, int32_t* parents, int32_t* steps, int32_t* hmap);
+                         int32_t n_lists, int64_t* n_groups, int64_t* n_steps, int64_t* n_slots,
+                         int32_t* root_slot, int32_t* groups, int32_t* parents, int32_t* steps,
+                         int32_t* hmap, int32_t* split);
 
 /* Row matching used by sample_on_SG's recycling (sparse_grid_interpolant.py:214-231): for
  * every row of `xx` (n x N) the index of the unique row of `old_xx` (n_old x N) with
@@ -217,6 +220,15 @@ int sgm_eval_signed_sum(sgm_plan* const* plans, const double* signs, int32_t n_p
  * alpha is M x ld (fp64, device), NF columns are updated. */
 int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, const int32_t* pa,
                    const int32_t* pb, const double* wa, const double* wb, int64_t n, void* stream);
+
+/* All batches of the hierarchisation in one call: batch b covers entries
+ * [batch_off[b], batch_off[b+1]) of the concatenated child / pa / pb / wa / wb arrays (device);
+ * batch_off is given both on the host and on the device (n_batches + 1 entries).  Small
+ * tables run as ONE launch of one block, large ones as one launch per batch. */
+int sgm_hier_apply_batches(double* alpha, int64_t NF, int64_t ld, const int32_t* child,
+                           const int32_t* pa, const int32_t* pb, const double* wa, const double* wb,
+                           const int64_t* batch_off_host, const int64_t* batch_off_dev,
+                           int32_t n_batches, void* stream);
 
 /* W[p, :] = Levy-Ciesielski expansion of Brownian motion on [0, T] at times tt for the
  * parameter vector yy[p, 0:d]  (reference: param_LC_Brownian_motion,

@@ -49,6 +49,8 @@ SIGNATURES = {
                                                ctypes.POINTER(c_vp)]),
     "sgm_hier_apply": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                       c_vp]),
+    "sgm_hier_apply_batches": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, p_i64,
+                                              c_vp, c_i32, c_vp]),
     "sgm_grid_num_nodes": (c_i64, [c_vp]),
     "sgm_grid_map_size": (c_i64, [c_vp]),
     "sgm_grid_nnz": (c_i64, [c_vp]),
@@ -56,8 +58,8 @@ SIGNATURES = {
     "sgm_grid_copy_nodes_dense": (ctypes.c_int, [c_vp, p_f64]),
     "sgm_grid_copy_nodes_csr": (ctypes.c_int, [c_vp, p_i64, p_i32, p_f64]),
     "sgm_grid_destroy": (None, [c_vp]),
-    "sgm_host_hier_groups": (ctypes.c_int, [c_i64, c_i32, p_i32, c_i32, p_i32, p_i64, p_i64, p_i64,
-                                            p_i64, p_i32, p_i32, p_i32, p_i32, p_i32]),
+    "sgm_host_hier_groups": (ctypes.c_int, [c_i64, c_i32, p_i32, c_i32, p_i32, p_i64, c_i32, p_i64,
+                                            p_i64, p_i64, p_i32, p_i32, p_i32, p_i32, p_i32, p_i32]),
     "sgm_host_match_rows": (ctypes.c_int, [p_f64, c_i64, p_f64, c_i64, c_i32, c_f64, p_i64]),
     "sgm_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.c_int,
                                        ctypes.POINTER(c_vp)]),
@@ -255,9 +257,10 @@ def match_rows(xx, old_xx, tol=1.e-10):
     return match
 
 
-def hier_groups(term_fam, fam_extent, val_off):
+def hier_groups(term_fam, fam_extent, val_off, n_lists=64):
     """Tables of the grouped hierarchical kernel (sgm_host_hier_groups): groups (n, 12),
-    parents (n, 8), steps (m, 2), hmap (slots,) int32 arrays and the root's slot."""
+    parents (n, 8), steps (m, 2), hmap (slots,) int32 arrays, the root's slot and the
+    n_lists + 1 bounds of the warps' group lists."""
     term_fam = np.ascontiguousarray(term_fam, dtype=np.int32)
     fam_extent = np.ascontiguousarray(fam_extent, dtype=np.int32)
     val_off = np.ascontiguousarray(val_off, dtype=np.int64)
@@ -265,12 +268,13 @@ def hier_groups(term_fam, fam_extent, val_off):
     ng, ns, nv, root = c_i64(0), c_i64(0), c_i64(0), c_i32(-1)
     none32 = ctypes.cast(None, p_i32)
     args = (T, N, ptr(term_fam, c_i32), fam_extent.size, ptr(fam_extent, c_i32), ptr(val_off, c_i64),
-            ctypes.byref(ng), ctypes.byref(ns), ctypes.byref(nv), ctypes.byref(root))
-    check(load().sgm_host_hier_groups(*args, none32, none32, none32, none32))
+            n_lists, ctypes.byref(ng), ctypes.byref(ns), ctypes.byref(nv), ctypes.byref(root))
+    check(load().sgm_host_hier_groups(*args, none32, none32, none32, none32, none32))
     groups = np.zeros((max(ng.value, 1), 12), dtype=np.int32)
     parents = np.zeros((max(ng.value, 1), 8), dtype=np.int32)
     steps = np.zeros((max(ns.value, 1), 2), dtype=np.int32)
     hmap = np.zeros(max(nv.value, 1), dtype=np.int32)
+    split = np.zeros(n_lists + 1, dtype=np.int32)
     check(load().sgm_host_hier_groups(*args, ptr(groups, c_i32), ptr(parents, c_i32),
-                                      ptr(steps, c_i32), ptr(hmap, c_i32)))
-    return groups[:ng.value], parents[:ng.value], steps[:ns.value], hmap[:nv.value], root.value
+                                      ptr(steps, c_i32), ptr(hmap, c_i32), ptr(split, c_i32)))
+    return groups[:ng.value], parents[:ng.value], steps[:ns.value], hmap[:nv.value], root.value, split

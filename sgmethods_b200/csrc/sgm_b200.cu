@@ -21,7 +21,8 @@ thread_local std::string g_last_error;
 bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
                            const int* fam_extent, const int64_t* val_off,
                            std::vector<int>& groups, std::vector<int>& parents,
-                           std::vector<int>& steps, std::vector<int>& hmap, int* root_slot);
+                           std::vector<int>& steps, std::vector<int>& hmap, int* root_slot,
+                           int n_lists, std::vector<int>& split);
 
 int sgm_fail(int code, const char* msg) {
     g_last_error = msg ? msg : "";
@@ -383,16 +384,16 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
         struct Shape { SplitKernel kern; int warps; };
         constexpr int NS = 6;
         const Shape shapes[NS] = {{sgm::eval_hier_groups_kernel<16, 2, 2, false>, 16},
-                                  {sgm::eval_hier_groups_kernel<14, 2, 2, false>, 14},
-                                  {sgm::eval_hier_groups_kernel<12, 2, 2, false>, 12},
+                                  {sgm::eval_hier_groups_kernel<16, 2, 2, true>, 16},
+                                  {sgm::eval_hier_groups_kernel<8, 4, 2, false>, 8},
                                   {sgm::eval_hier_groups_kernel<8, 3, 2, false>, 8},
                                   {sgm::eval_hier_groups_kernel<16, 1, 2, false>, 16},
-                                  {sgm::eval_hier_groups_kernel<12, 2, 4, false>, 12}};
+                                  {sgm::eval_hier_groups_kernel<16, 2, 4, false>, 16}};
         const PlanDev& d = plan->dev;
         for (int si = 0; si < NS; ++si) {
             const Shape& sh = shapes[(si + plan->knobs.h2_shape) % NS];
-            const size_t smem = (size_t)d.n_knots * 16 + (size_t)(d.B + 1) * 32 * 8 + (size_t)sh.warps * 32 * 8 +
-                                (size_t)(d.E + 1) * 32 * 2 + 64 + 16;
+            const size_t smem = (size_t)d.n_knots * 16 + (size_t)(d.B + 1) * 32 * 8 +
+                                (size_t)sgm::H2_LISTS * (32 * 8 + 4) + (size_t)(d.E + 1) * 32 * 2 + 64 + 64;
             if (smem > (size_t)plan->max_smem_optin ||
                 cudaFuncSetAttribute(sh.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 continue;
@@ -1124,15 +1125,16 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     if (kind == SGM_HIER_PW_LINEAR)
         for (int64_t i = 0; i < n_knots; ++i) newrank.push_back((short)desc->fam_newrank[i]);
     // grouped hierarchical kernel: group / step tables over the trie of the multi-indices
-    std::vector<int> h2_groups, h2_parents, h2_steps, h2_maps;
+    std::vector<int> h2_groups, h2_parents, h2_steps, h2_maps, h2_split;
     int h2_root = -1;
     if (kind == SGM_HIER_PW_LINEAR && T > 0) {
         if (sgm_build_hier_groups(T, N, desc->term_fam, desc->n_fam, fam_extent.data(), desc->map_off,
-                                  h2_groups, h2_parents, h2_steps, h2_maps, &h2_root)) {
+                                  h2_groups, h2_parents, h2_steps, h2_maps, &h2_root, sgm::H2_LISTS,
+                                  h2_split)) {
             for (int& v : h2_maps)                      // slot -> row of f through the caller's map
                 if (v >= 0) v = desc->maps[v];
         } else {
-            h2_groups.clear(); h2_parents.clear(); h2_steps.clear(); h2_maps.clear();
+            h2_groups.clear(); h2_parents.clear(); h2_steps.clear(); h2_maps.clear(); h2_split.clear();
         }
     }
     std::vector<unsigned> flags(4, 0u);
@@ -1149,6 +1151,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         (rc = upload(plan, lambda, &d.lambda)) || (rc = upload(plan, newrank, &d.newrank)) ||
         (rc = upload(plan, h2_groups, &h2g)) || (rc = upload(plan, h2_parents, &h2p)) ||
         (rc = upload(plan, h2_steps, &d.h2_steps)) || (rc = upload(plan, h2_maps, &d.h2_maps)) ||
+        (rc = upload(plan, h2_split, &d.h2_split)) ||
         (rc = upload(plan, flags, &cflags))) {
         sgm_plan_destroy(plan);
         return rc;
@@ -1315,6 +1318,35 @@ int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, 
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     sgm::hier_apply_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         alpha, NF, ld, child, pa, pb, wa, wb, n);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+int sgm_hier_apply_batches(double* alpha, int64_t NF, int64_t ld, const int32_t* child,
+                           const int32_t* pa, const int32_t* pb, const double* wa, const double* wb,
+                           const int64_t* batch_off_host, const int64_t* batch_off_dev,
+                           int32_t n_batches, void* stream) {
+    if (n_batches < 0 || NF < 1 || ld < NF) return sgm_fail(SGM_ERR_INVALID, "hier_apply_batches: bad shapes");
+    if (n_batches == 0) return SGM_OK;
+    if (!alpha || !batch_off_host || !batch_off_dev)
+        return sgm_fail(SGM_ERR_INVALID, "hier_apply_batches: null buffer");
+    const int64_t total = batch_off_host[n_batches];
+    if (total == 0) return SGM_OK;
+    if (!child || !pa || !pb || !wa || !wb) return sgm_fail(SGM_ERR_INVALID, "hier_apply_batches: null buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total * NF <= ((int64_t)1 << 20)) {        // one block walks all batches
+        sgm::hier_apply_all_kernel<<<1, 1024, 0, st>>>(alpha, NF, ld, child, pa, pb, wa, wb,
+                                                       batch_off_dev, n_batches);
+        SGM_CUDA(cudaGetLastError());
+        return SGM_OK;
+    }
+    for (int b = 0; b < n_batches; ++b) {           // large tables: one launch per batch
+        const int64_t lo = batch_off_host[b], n = batch_off_host[b + 1] - lo;
+        if (n <= 0) continue;
+        const int blocks = (int)std::min<int64_t>((n * NF + 255) / 256, 148 * 16);
+        sgm::hier_apply_kernel<<<blocks, 256, 0, st>>>(alpha, NF, ld, child + lo, pa + lo, pb + lo,
+                                                       wa + lo, wb + lo, n);
+    }
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
 }

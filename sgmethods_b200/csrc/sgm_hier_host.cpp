@@ -25,14 +25,22 @@
 //                    the parent's block), [3] S_mem (size of a member's block = stride of the
 //                    leaf direction), [4..7] member entries * 64 (8 x u16; unused slots and the
 //                    root group's "member = the parent itself" name the DUMMY entry n_entries,
-//                    whose hat value is 1 and rank 0), [8..11] 8 x u16: the steps are listed by
+//                    whose hat value is 1 and rank 0), [8..10] 6 x u16: the steps are listed by
 //                    decreasing nv (then by slot size), entry i = first step (relative) with
-//                    fewer than 7 - i members present;
+//                    fewer than 7 - i members present; [1] bits 24..29 and [11]: see below;
 //   parent (8 ints): word j = entry_j * 64 | extent_j << 16 along the parent's path;
 //   step (2 ints):   [0] sbase, [1] entry * 64 | slot << 16.
-// Groups are listed by decreasing cost: the kernel's warps take them from a shared counter.
+// EXECUTION is dynamic -- the groups are stored by decreasing cost and the warps of a block take
+// them from a shared counter, so that all warps reach the end-of-tile barrier together -- but
+// the SUMMATION order is static: the groups are dealt to `n_lists` lists (heaviest first, each
+// to the list with the least load; group word [1] bits 24..29 = list, word [11] = position in
+// the list), the kernel adds a group's result to its list's accumulator in list order
+// (a ticket per list) and adds the lists up in order.  The result bits therefore do not
+// depend on which warp ran which group.  split[w] = number of groups in lists < w.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -65,13 +73,15 @@ struct Group {
 bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
                            const int* fam_extent, const int64_t* val_off,
                            std::vector<int>& groups, std::vector<int>& parents,
-                           std::vector<int>& steps, std::vector<int>& hmap, int* root_slot) {
+                           std::vector<int>& steps, std::vector<int>& hmap, int* root_slot,
+                           int n_lists, std::vector<int>& split) {
+    split.clear();
     groups.clear();
     parents.clear();
     steps.clear();
     hmap.clear();
     *root_slot = -1;
-    if (T <= 0 || n_fam <= 0) return false;
+    if (T <= 0 || n_fam <= 0 || n_lists < 1 || n_lists > 64) return false;
     std::vector<int> entry_of((size_t)N * n_fam, -1);
     std::vector<int> ent_fam;                                 // family of every entry
     std::vector<std::vector<int>> path((size_t)T);
@@ -112,6 +122,9 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
     };
     std::vector<Group> all;
     bool ok = true;
+    double cost_w[4] = {800.0, 60.0, 250.0, 10.0};
+    if (const char* env = std::getenv("SGM_H2_COST"))
+        std::sscanf(env, "%lf,%lf,%lf,%lf", &cost_w[0], &cost_w[1], &cost_w[2], &cost_w[3]);
     auto emit_group = [&](int parent, const std::vector<int>& members) {
         // members: internal nodes whose parent is `parent`, child sets nested in this order;
         // parent < 0: the root itself is the only member
@@ -147,7 +160,7 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
         std::sort(sweep.begin(), sweep.end());
         if (sweep.size() > 0xffff) { ok = false; return; }
         unsigned short* bounds = reinterpret_cast<unsigned short*>(G.g + 8);
-        for (int i = 0; i < 8; ++i) {                          // first step with nv < 7 - i
+        for (int i = 0; i < 6; ++i) {                          // first step with nv < 7 - i
             size_t sidx = 0;
             while (sidx < sweep.size() && -sweep[sidx].first.first >= 7 - i) ++sidx;
             bounds[i] = (unsigned short)sidx;
@@ -172,9 +185,11 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
         G.g[1] = (int)(G.step_words.size() / 2) | ((int)members.size() << 16) | (n_par << 20);
         G.g[2] = (int)S_par;
         G.g[3] = (int)S_mem;
-        // L1 data-pipe wavefronts: header, parent and member prefixes, step reads, gathers
-        G.cost = 8.0 + (n_par ? 8.0 + 3.0 * n_par : 0.0) + 3.0 * members.size() +
-                 5.0 * (G.step_words.size() / 2) + 2.5 * leaves;
+        // time of a group on one warp, in cycles: a warp is latency-bound, so a step costs
+        // about one dependent shared-memory read plus one gather round trip whatever the number
+        // of members, and every group pays its header / prefix chain (dev knob SGM_H2_COST =
+        // "group,parent entry,step,leaf")
+        G.cost = cost_w[0] + cost_w[1] * n_par + cost_w[2] * (G.step_words.size() / 2) + cost_w[3] * leaves;
         all.push_back(std::move(G));
     };
     if (!kids[root].empty()) emit_group(-1, {root});
@@ -210,8 +225,24 @@ bool sgm_build_hier_groups(int64_t T, int N, const int32_t* term_fam, int n_fam,
         for (int c : internal) stack.push_back(c);
     }
     if (!ok) return false;
-    // value layout: slot 0 = the root's surplus, then the groups (16-aligned) by decreasing cost
+    // deal the groups to the lists: heaviest first, each to the list with the least load
     std::stable_sort(all.begin(), all.end(), [](const Group& a, const Group& b) { return a.cost > b.cost; });
+    {
+        std::vector<double> load((size_t)n_lists, 0.0);
+        std::vector<int> list_of(all.size());
+        for (size_t i = 0; i < all.size(); ++i) {
+            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            list_of[i] = w;
+            load[w] += all[i].cost;
+        }
+        split.assign((size_t)n_lists + 1, 0);
+        for (size_t i = 0; i < all.size(); ++i) {
+            all[i].g[1] |= list_of[i] << 24;
+            all[i].g[11] = split[(size_t)list_of[i] + 1]++;        // position in its list
+        }
+        for (int w = 0; w < n_lists; ++w) split[w + 1] += split[w];
+    }
+    // value layout: slot 0 = the root's surplus, then the groups (16-aligned) in table order
     int64_t total = 16;
     for (const Group& G : all) total += (G.vals + 15) / 16 * 16;
     if (total > 0x7fffffff) return false;
@@ -239,14 +270,15 @@ extern "C" {
 
 int sgm_host_hier_groups(int64_t T, int32_t N, const int32_t* term_fam, int32_t n_fam,
                          const int32_t* fam_extent, const int64_t* val_off,
-                         int64_t* n_groups, int64_t* n_steps, int64_t* n_slots, int32_t* root_slot,
-                         int32_t* groups, int32_t* parents, int32_t* steps, int32_t* hmap) {
-    if (T < 0 || N <= 0 || n_fam < 0 || !n_groups || !n_steps || !n_slots || !root_slot ||
+                         int32_t n_lists, int64_t* n_groups, int64_t* n_steps, int64_t* n_slots,
+                         int32_t* root_slot, int32_t* groups, int32_t* parents, int32_t* steps,
+                         int32_t* hmap, int32_t* split) {
+    if (T < 0 || N <= 0 || n_fam < 0 || n_lists < 1 || !n_groups || !n_steps || !n_slots || !root_slot ||
         (T > 0 && (!term_fam || !val_off)) || (n_fam > 0 && !fam_extent))
         return sgm_fail(SGM_ERR_INVALID, "hier_groups: bad argument");
-    std::vector<int> g, p, s, h;
+    std::vector<int> g, p, s, h, sp;
     int root = -1;
-    if (!sgm_build_hier_groups(T, N, term_fam, n_fam, fam_extent, val_off, g, p, s, h, &root))
+    if (!sgm_build_hier_groups(T, N, term_fam, n_fam, fam_extent, val_off, g, p, s, h, &root, n_lists, sp))
         return sgm_fail(SGM_ERR_INVALID, "hier_groups: the multi-index set cannot be grouped "
                                          "(not downward closed, or more than 9 active directions)");
     *n_groups = (int64_t)g.size() / 12;
@@ -257,6 +289,7 @@ int sgm_host_hier_groups(int64_t T, int32_t N, const int32_t* term_fam, int32_t 
     if (parents) std::memcpy(parents, p.data(), p.size() * sizeof(int));
     if (steps) std::memcpy(steps, s.data(), s.size() * sizeof(int));
     if (hmap) std::memcpy(hmap, h.data(), h.size() * sizeof(int));
+    if (split) std::memcpy(split, sp.data(), sp.size() * sizeof(int));
     return SGM_OK;
 }
 

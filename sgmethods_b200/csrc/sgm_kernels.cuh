@@ -78,6 +78,7 @@ struct PlanDev {
     const int* h2_parents;             // 8 ints per group
     const int* h2_steps;               // 2 ints per step
     const int* h2_maps;                // value slot of the H2 layout -> row of f (-1: padding)
+    const int* h2_split;               // H2_LISTS + 1 group bounds: list w = groups [split[w], split[w+1])
     int h2_n_groups, h2_n_vals;
     int h2_root_off;                   // slot of the root's surplus in the H2 value table (-1: none)
     unsigned* flags;
@@ -910,7 +911,11 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 // two 16-byte record loads per gather -- and a warp-wide load of UNIFORM data costs the pipe
 // 32 x its size, which is why the records here are 8 bytes per step and nothing per gather.
 // The warps of a block take groups from a shared counter (listed by decreasing cost), so the
-// end-of-tile barrier waits for at most one small group.
+// end-of-tile barrier waits for at most one small group.  The SUM is nevertheless formed in a
+// fixed order: every group belongs to one of H2_LISTS lists with a position in it; its result
+// is added to the list's shared-memory accumulator when the list's ticket reaches that position
+// (the earlier groups of a list were taken earlier, by warps that are running: no deadlock),
+// and the lists are added in order.  Same bits whichever warp ran which group.
 // The order of the sum is not the reference's: this form makes no bit-exactness claim
 // (DESIGN.md 5.1), it is proven <= 1e-12 against the reference.
 // ---------------------------------------------------------------------------------------
@@ -968,6 +973,7 @@ __device__ __forceinline__ void hier_sweep(const int2* __restrict__ st, int s0, 
     }
 }
 
+constexpr int H2_LISTS = 64;           // summation lists the groups are dealt to
 template <int W, int MINB, int UNROLL, bool CONTIG>
 __global__ void __launch_bounds__(W * 32, MINB)
 eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
@@ -986,16 +992,17 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
     // bracket tables [E + 1][32]: row E is the DUMMY entry (hat value 1, rank 0) that unused
     // member slots and the root group point to, so the member set-up needs no predicates
     double* bas_all = sknots + 2 * (size_t)pl.n_knots;
-    double* sPart = bas_all + (size_t)(pl.B + 1) * 32;        // [W][32]
-    unsigned short* idx_all = reinterpret_cast<unsigned short*>(sPart + (size_t)W * 32);
-    int* sCounter = reinterpret_cast<int*>(idx_all + (size_t)(pl.E + 1) * 32);
+    unsigned short* idx_all = reinterpret_cast<unsigned short*>(bas_all + (size_t)(pl.B + 1) * 32);
+    double* sAcc = reinterpret_cast<double*>(idx_all + (size_t)(pl.E + 1) * 32);   // [H2_LISTS][32]
+    volatile int* sTicket = reinterpret_cast<volatile int*>(sAcc + H2_LISTS * 32);    // [H2_LISTS]
+    int* sCounter = const_cast<int*>(sTicket) + H2_LISTS;
+    const int n_groups = pl.h2_n_groups;
     if (threadIdx.x < 32) {
         bas_all[(size_t)pl.B * 32 + threadIdx.x] = 1.0;
         idx_all[(size_t)pl.E * 32 + threadIdx.x] = 0;
     }
     const unsigned char* ybase = reinterpret_cast<const unsigned char*>(bas_all + lane);
     const unsigned char* ibase = reinterpret_cast<const unsigned char*>(idx_all + lane);
-    const int n_groups = pl.h2_n_groups;
     const int2* all_steps = reinterpret_cast<const int2*>(pl.h2_steps);
 
     const int64_t n_tiles = (P + 31) >> 5;
@@ -1014,9 +1021,10 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
                                              idx_all + lane, e, 32, pl.flags);
         }
+        for (int i = threadIdx.x; i < H2_LISTS * 32; i += blockDim.x) sAcc[i] = 0.0;
+        if (threadIdx.x < H2_LISTS) sTicket[threadIdx.x] = 0;
         if (threadIdx.x == 0) *sCounter = 0;
         __syncthreads();
-        double total = (warp == 0 && pl.h2_root_off >= 0) ? __ldg(A + pl.h2_root_off) : 0.0;
 #pragma unroll 1
         for (;;) {
             int gi = 0;
@@ -1027,7 +1035,7 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             const int4 h0 = ldg_keep(gh);    // first step, steps | n_mem << 16 | n_par << 20, S_par, S_mem
             const int4 h1 = ldg_keep(gh + 1);// member entries * 64 (8 x u16; unused: the dummy entry)
             const int4 h2 = ldg_keep(gh + 2);// step bounds per member count (8 x u16)
-            const int n_steps = h0.y & 0xffff, n_par = (h0.y >> 20) & 0xf;
+            const int n_steps = h0.y & 0xffff, n_par = (h0.y >> 20) & 0xf;   // (bits 24..29: list)
             double w_par = 1.0;
             int off_par = 0;
             {                                // the parent's path: entry * 64 | extent << 16 per word
@@ -1073,14 +1081,21 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
                 const unsigned e64 = (g & 1) ? me[g >> 1] >> 16 : me[g >> 1] & 0xffffu;
                 gsum = fma(*reinterpret_cast<const double*>(ybase + 4u * e64), acc[g], gsum);
             }
-            total = fma(w_par, gsum, total);
+            {   // add to the group's list in list order (ticket = position in the list)
+                const int list = (h0.y >> 24) & 0x3f, pos = h2.w;
+                while (sTicket[list] != pos) {}
+                volatile double* slot = sAcc + list * 32 + lane;
+                *slot = *slot + w_par * gsum;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) sTicket[list] = pos + 1;
+            }
         }
-        sPart[warp * 32 + lane] = total;
         __syncthreads();
         if (warp == 0 && valid) {
-            double o = 0.0;
+            double o = pl.h2_root_off >= 0 ? __ldg(A + pl.h2_root_off) : 0.0;
 #pragma unroll
-            for (int ww = 0; ww < W; ++ww) o = o + sPart[ww * 32 + lane];
+            for (int ww = 0; ww < H2_LISTS; ++ww) o = o + sAcc[ww * 32 + lane];
             double* dst = out + p * ldo;
             *dst = accumulate ? *dst + scale * o : scale * o;
         }
@@ -1652,6 +1667,28 @@ __global__ void hier_apply_kernel(double* __restrict__ alpha, int64_t NF, int64_
         double coarse = wa[it] * alpha[(int64_t)pa[it] * ld + c];
         if (pb[it] >= 0) coarse = coarse + wb[it] * alpha[(int64_t)pb[it] * ld + c];
         alpha[(int64_t)child[it] * ld + c] -= coarse;
+    }
+}
+
+// All hierarchisation batches in ONE launch of ONE block (small tables: the batches are
+// sequential, a block-wide barrier separates them; 64 launches of a few microseconds of work
+// each cost more than the work).
+__global__ void __launch_bounds__(1024)
+hier_apply_all_kernel(double* __restrict__ alpha, int64_t NF, int64_t ld,
+                      const int* __restrict__ child, const int* __restrict__ pa,
+                      const int* __restrict__ pb, const double* __restrict__ wa,
+                      const double* __restrict__ wb, const int64_t* __restrict__ batch_off,
+                      int n_batches) {
+    for (int b = 0; b < n_batches; ++b) {
+        const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
+        const int64_t total = n * NF;
+        for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const int64_t it = lo + i / NF, c = i % NF;
+            double coarse = wa[it] * alpha[(int64_t)pa[it] * ld + c];
+            if (pb[it] >= 0) coarse = coarse + wb[it] * alpha[(int64_t)pb[it] * ld + c];
+            alpha[(int64_t)child[it] * ld + c] -= coarse;
+        }
+        __syncthreads();
     }
 }
 

@@ -296,25 +296,85 @@ class SGInterpolant:
                                     "active direction")
 
     def hierarchical(self):
-        """The opt-in work-reduced evaluator (pw-linear, nested knots): see hierarchical.py."""
+        """The work-reduced evaluator (pw-linear, nested knots): see hierarchical.py."""
         if getattr(self, "_hier", None) is None:
             from .hierarchical import HierarchicalPlan
             self._hier = HierarchicalPlan(self)
         return self._hier
 
-    def interpolate(self, x_new, f_on_SG, method="combination"):
+    # --------------------------------------------------------------- method selection
+    def _auto_candidate(self, host_rows):
+        """The hierarchical plan if ``method="auto"`` may use it for a batch of ``host_rows``
+        points, else None: the form exists for pw-linear operators on nested knots only
+        (hierarchical.py), small batches stay on the exact kernels (they are latency-bound
+        either way and the exact path is bit-identical), and an interpolant on which the form
+        once failed its validation keeps the exact kernels."""
+        if self._kind != _lib.KIND_LINEAR or host_rows < AUTO_MIN_POINTS or \
+                getattr(self, "_auto_choice", None) == "combination":
+            return None
+        try:
+            return self.hierarchical()
+        except NotImplementedError as exc:
+            self._auto_choice = "combination"
+            self.auto_validation = {"enabled": False, "reason": str(exc)}
+            return None
+
+    def _auto_validation_launch(self, torch, hp, x_new, f, alpha, device, host_rows):
+        """Enqueue the validation of the hierarchical form for THIS call: both kernels evaluate
+        a sample of the batch (up to AUTO_SAMPLE rows spread over it) with the caller's nodal
+        values; max|hier - exact| / max|exact| goes to a pinned host scalar.  Returns
+        (pinned scalar, event recorded after its copy)."""
+        step = max(1, host_rows // AUTO_SAMPLE)
+        xs = x_new[::step][:AUTO_SAMPLE]
+        if isinstance(xs, np.ndarray):
+            xs = np.ascontiguousarray(xs[:, :self.N])
+        xs = _to_device(torch, xs, device)
+        if xs.shape[1] > self.N:
+            xs = xs[:, :self.N].contiguous()
+        exact = self.device_plan(device.index).eval(xs, f)
+        fast = hp._dev(device.index)[0].eval(xs, alpha)
+        scale = exact.abs().max()
+        dev = (fast - exact).abs().max() / torch.where(scale > 0, scale, torch.ones_like(scale))
+        host = getattr(self, "_auto_host", None)
+        if host is None:
+            host = self._auto_host = torch.empty(1, dtype=torch.float64).pin_memory()
+        host.copy_(dev.reshape(1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(device))
+        return host, done, int(xs.shape[0])
+
+    def _auto_verdict(self, host, done, n_sample):
+        done.synchronize()                   # waits for the small validation launches only
+        dev = float(host[0])
+        ok = bool(np.isfinite(dev)) and dev <= AUTO_TOL
+        self.auto_validation = {"enabled": ok, "max_rel_deviation": dev, "tolerance": AUTO_TOL,
+                                "sample_points": n_sample}
+        self._auto_choice = "hierarchical" if ok else "combination"     # a failure is sticky
+        return ok
+
+    def interpolate(self, x_new, f_on_SG, method=None):
         """Evaluate the interpolant at the rows of ``x_new`` (only the first N columns are
         read) for the nodal values ``f_on_SG`` (num_nodes, dim_f).
 
         numpy in -> numpy out (``np.squeeze``d like the reference, :279); CUDA torch tensors
         in -> CUDA tensor out without host round trips.  One fused kernel launch.
-        ``method="combination"`` (default) is the reference's formula, bit for bit;
-        ``method="hierarchical"`` is the opt-in work-reduced form (same function, agrees to
-        about the reference's own rounding error, ~10x fewer gathers; hierarchical.py)."""
-        if method == "hierarchical":
-            return self.hierarchical().interpolate(x_new, f_on_SG)
-        if method != "combination":
-            raise ValueError("method must be 'combination' or 'hierarchical'")
+
+        ``method``:
+          * ``"combination"`` -- the reference's combination formula, bit for bit
+            (sparse_grid_interpolant.py:268-279 with the operators' own arithmetic order);
+          * ``"hierarchical"`` -- the work-reduced hierarchical-surplus form (pw-linear, nested
+            knots; hierarchical.py): the same function with ~10x fewer gathers, agreeing with
+            the reference to about the reference's own rounding error;
+          * ``"auto"`` (the default, ``DEFAULT_METHOD``) -- the hierarchical form when it exists,
+            the batch is large and THIS call's validation passes: a sample of the batch is
+            evaluated by both kernels with the caller's nodal values and must agree to
+            ``AUTO_TOL`` = 2.5e-13 (4x inside the 1e-12 contract; the deviation is the
+            reference's own cancellation error, which depends on the data -- config 5 with
+            smooth values reaches 1e-11 and therefore stays on the exact kernel).  Otherwise
+            the exact kernel.  The last outcome is in ``auto_validation``."""
+        method = DEFAULT_METHOD if method is None else method
+        if method not in ("auto", "combination", "hierarchical"):
+            raise ValueError("method must be 'auto', 'combination' or 'hierarchical'")
         from ._device import torch_cuda
         torch = torch_cuda()
         self._check_operator_constraints()
@@ -330,14 +390,27 @@ class SGInterpolant:
             raise IndexError("f_on_SG must be 2-D (num_nodes, dim_f)")     # reference: tuple index out of range
         if f.shape[0] < self.num_nodes:
             raise IndexError(f"f_on_SG has {f.shape[0]} rows, the sparse grid {self.num_nodes}")
-        plan = self.device_plan(device.index)
         host_rows = x_new.shape[0] if hasattr(x_new, "shape") and len(x_new.shape) == 2 else 0
+        if host_rows and x_new.shape[1] < n_used:
+            raise IndexError(f"x_new has {x_new.shape[1]} columns, the interpolant uses {n_used}")
+        exact_plan = self.device_plan(device.index)
+        plan, f_eval, pending = exact_plan, f, None
+        hp = self.hierarchical() if method == "hierarchical" else \
+            (self._auto_candidate(host_rows) if method == "auto" else None)
+        if hp is not None:
+            plan = hp._dev(device.index)[0]
+            f_eval = hp.surpluses(f[:hp.M])      # nodal values -> hierarchical surpluses (GPU)
+            if method == "auto":
+                pending = self._auto_validation_launch(torch, hp, x_new, f, f_eval, device, host_rows)
         pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
             x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
         big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
             x_new.dtype == np.float64 and x_new.shape[1] >= self.N
         if (pinned or big_numpy) and host_rows >= 4 * _H2D_CHUNK:
-            out = self._interpolate_pipelined(torch, plan, x_new, f, device)
+            if pending is not None and not self._auto_verdict(*pending):
+                plan, f_eval = exact_plan, f
+            pending = None
+            out = self._interpolate_pipelined(torch, plan, x_new, f_eval, device)
         else:
             if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):
                 x_new = x_new[:, :self.N]        # only the first N columns travel to the GPU
@@ -348,7 +421,9 @@ class SGInterpolant:
                 raise IndexError(f"x_new has {x.shape[1]} columns, the interpolant uses {n_used}")
             if x.shape[1] < self.N:      # unused trailing directions: pad so that ldx >= N
                 x = torch.nn.functional.pad(x, (0, self.N - x.shape[1]))
-            out = plan.eval(x, f)
+            out = plan.eval(x, f_eval)           # enqueued before the verdict is read: it overlaps
+            if pending is not None and not self._auto_verdict(*pending):
+                out = exact_plan.eval(x, f, out)             # validation failed: the exact kernel
         if self._kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
                              "(or is NaN); the reference raises IndexError here "
@@ -356,6 +431,14 @@ class SGInterpolant:
         if as_torch:
             return out.squeeze()
         return np.squeeze(out.cpu().numpy())
+
+
+# ``interpolate(..., method=None)`` uses this; "auto" = fastest form that is validated to meet
+# the 1e-12 contract, "combination" = always the reference's formula bit for bit.
+DEFAULT_METHOD = "auto"
+AUTO_MIN_POINTS = 8192      # smaller batches stay on the exact kernels
+AUTO_SAMPLE = 256           # rows of the first large batch evaluated by both kernels
+AUTO_TOL = 2.5e-13          # max |hier - exact| / max |exact| that enables the form
 
 
 # rows per host->device chunk of the pipelined path: a whole number of waves of the scalar

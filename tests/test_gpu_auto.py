@@ -1,0 +1,220 @@
+"""The contract path of ``SGInterpolant.interpolate``: ``method="auto"`` and the work-reduced
+hierarchical-surplus form it selects -- needs a B200.
+
+The north star's bar is max|gpu - ref| / max|ref| <= 1e-12 against the reference's
+numpy/scipy path.  The hierarchical form is not bit-identical to the reference (it is the
+same function evaluated without the large alternating combination sum), so every test here
+states the tolerance: 1e-12, on the reference's own outputs (tests/golden), on the CPU oracle
+(pinned to those outputs) and, for point counts the oracle cannot do, on the bit-exact CUDA
+path (itself pinned in test_gpu_parity.py).  Shapes: BASELINE configs 2, 3 and 5, random and
+smooth nodal values.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from golden_cases import CASES, LEV2KNOTS, knot_family
+from oracle import sg_oracle
+from sgmethods_b200 import multi_index_sets as mis, nodes_1d
+from sgmethods_b200 import sparse_grid_interpolant as sgi
+from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
+from sgmethods_b200.utils import compute_level_lc
+
+pytestmark = pytest.mark.gpu
+TOL = 1.e-12                      # BASELINE.json north_star tolerance
+L2K = lambda n: 2 ** (n + 1) - 1  # noqa: E731
+
+
+def rel_dev(got, ref):
+    got, ref = np.asarray(got, dtype=float), np.asarray(ref, dtype=float)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.max(np.abs(ref[ok])) if ok.any() else 1.0
+    return float(np.max(np.abs(got[ok] - ref[ok])) / (scale if scale > 0 else 1.0)) if ok.any() else 0.0
+
+
+def oracle_plan_of(it):
+    return sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
+                                      it.active_tp_nodes_list, it.map_tp_to_SG)
+
+
+def smooth_values(it, NF=1):
+    """sin(sum_n y_n / n^2) (the reference's example function, example/0 :27-29) and shifts."""
+    w = 1.0 / np.arange(1, it.N + 1) ** 2
+    s = it.SG @ w
+    return np.stack([np.sin(s + 0.3 * c) for c in range(NF)], axis=1)
+
+
+def config2(w=4):
+    return SGInterpolant(mis.smolyak_mid_set(w, 16), nodes_1d.unbounded_nodes_nested, L2K, verbose=False)
+
+
+def config3(w=8):
+    a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
+    return SGInterpolant(mis.aniso_smolyak_mid_set(w, 64, a),
+                         lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2), L2K, verbose=False)
+
+
+def config5():
+    S = mis.aniso_smolyak_mid_set(3, 128, np.array([1.0] * 80 + [3.0] * 48))
+    return SGInterpolant(S, nodes_1d.unbounded_nodes_nested, L2K, verbose=False)
+
+
+# ------------------------------------------------------------ reference outputs (golden)
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c[2] == "linear"))
+def test_hierarchical_form_on_reference_outputs(name):
+    """Every pw-linear fixture: where the hierarchical form exists it reproduces the REFERENCE's
+    output to 1e-12 (incl. NaN inputs and extrapolation); where it does not, it says so and
+    method='auto' is the exact kernel."""
+    fam, l2k, kind = CASES[name]
+    g = load_golden(name)
+    it = SGInterpolant(g["mid_set"], knot_family(fam, nodes_1d), LEV2KNOTS[l2k], verbose=False)
+    try:
+        out = it.interpolate(g["x"], g["f_on_SG"], method="hierarchical")
+    except NotImplementedError:
+        assert name in ("lin_deg1", "lin_exp_cc", "lin_example0")      # not nested / lev2knots(0) != 1
+        out = it.interpolate(g["x"], g["f_on_SG"], method="auto")
+        assert np.array_equal(out, it.interpolate(g["x"], g["f_on_SG"], method="combination"), equal_nan=True)
+    assert rel_dev(out, g["out"]) <= TOL
+
+
+# ------------------------------------------------------------ configs 2 / 3 / 5 shapes
+@pytest.mark.parametrize("data", ["random", "smooth"])
+def test_config2_shape_hierarchical_within_contract(data):
+    it = config2()
+    rng = np.random.default_rng(3)
+    f = rng.normal(size=(it.num_nodes, 1)) if data == "random" else smooth_values(it)
+    x = rng.normal(size=(60000, 16))
+    x[:8] *= 4.0                                         # far outside the knots: extrapolation
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:48], f)
+    fast = it.interpolate(x, f, method="hierarchical")
+    exact = it.interpolate(x, f, method="combination")
+    assert np.array_equal(exact[:48], ref)               # the exact path is the reference, bit for bit
+    print(f"config-2 {data}: hierarchical vs reference arithmetic {rel_dev(fast, exact):.2e}")
+    assert rel_dev(fast[:48], ref) <= TOL
+    assert rel_dev(fast, exact) <= TOL
+
+
+@pytest.mark.parametrize("data", ["random", "smooth"])
+@pytest.mark.parametrize("NF", [1, 320])
+def test_config3_shape_hierarchical_within_contract(data, NF):
+    it = config3()
+    rng = np.random.default_rng(4)
+    f = rng.normal(size=(it.num_nodes, NF)) if data == "random" else smooth_values(it, NF)
+    x = rng.normal(size=(9000 if NF == 1 else 4200, 64))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:24], f, squeeze=False)
+    fast = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(x.shape[0], NF)
+    exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(x.shape[0], NF)
+    print(f"config-3 NF={NF} {data}: hierarchical vs reference arithmetic {rel_dev(fast, exact):.2e}")
+    assert rel_dev(fast[:24], ref) <= TOL
+    assert rel_dev(fast, exact) <= TOL
+
+
+def test_config5_shape_auto_stays_within_contract_for_random_and_smooth_data():
+    """d = 128, 91 929 terms, sum |c| = 6.7e5: where the reference's own cancellation error is
+    largest.  With random nodal values the hierarchical form agrees with the reference
+    arithmetic to ~1e-13 and method="auto" uses it; with smooth values the REFERENCE's
+    rounding error is ~1e-11 (the form is the more accurate of the two, see the long-double
+    test in test_gpu_parity.py), so the form is outside the 1e-12 contract, the per-call
+    validation rejects it and "auto" returns the exact kernel's result.  The oracle does 4
+    points (91 929 scipy calls each); 20 000 points against the bit-exact CUDA path."""
+    it = config5()
+    assert len(it.combination_coeffs) == 91929
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(20000, 128))
+    plan = oracle_plan_of(it)
+    f = rng.normal(size=(it.num_nodes, 1))
+    exact = it.interpolate(x, f, method="combination")
+    assert np.array_equal(exact[:4], sg_oracle.interpolate(plan, x[:4], f))
+    auto = it.interpolate(x, f)
+    print(f"config-5 random: {it.auto_validation}, auto vs reference arithmetic {rel_dev(auto, exact):.2e}")
+    assert it.auto_validation["enabled"] and rel_dev(auto, exact) <= TOL
+    fs = smooth_values(it)
+    exact = it.interpolate(x, fs, method="combination")
+    assert np.array_equal(exact[:4], sg_oracle.interpolate(plan, x[:4], fs))
+    fast = it.interpolate(x, fs, method="hierarchical")
+    auto = it.interpolate(x, fs)
+    print(f"config-5 smooth: {it.auto_validation}, hierarchical vs reference arithmetic "
+          f"{rel_dev(fast, exact):.2e}")
+    assert not it.auto_validation["enabled"]
+    assert np.array_equal(auto, exact)                   # the exact kernel answered
+    assert rel_dev(fast, exact) <= 1e-10                 # same function; the gap is rounding
+
+
+# ------------------------------------------------------------ method="auto"
+def test_auto_is_the_default_and_validates_before_switching():
+    assert sgi.DEFAULT_METHOD == "auto"
+    it = config2(3)
+    rng = np.random.default_rng(6)
+    f = rng.normal(size=(it.num_nodes, 1))
+    small = rng.normal(size=(500, 16))
+    # small batches: the exact kernel, bit-identical to the reference arithmetic
+    assert np.array_equal(it.interpolate(small, f), sg_oracle.interpolate(oracle_plan_of(it), small, f))
+    assert getattr(it, "_auto_choice", None) is None
+    big = rng.normal(size=(40000, 16))
+    got = it.interpolate(big, f)                          # large batch: validated, then used
+    assert it.auto_validation["enabled"] and it._auto_choice == "hierarchical"
+    assert it.auto_validation["sample_points"] <= sgi.AUTO_SAMPLE
+    assert it.auto_validation["max_rel_deviation"] <= sgi.AUTO_TOL
+    assert np.array_equal(got, it.interpolate(big, f, method="hierarchical"))
+    assert rel_dev(got, it.interpolate(big, f, method="combination")) <= TOL
+    # small batches stay exact afterwards as well
+    assert np.array_equal(it.interpolate(small, f), it.interpolate(small, f, method="combination"))
+    with pytest.raises(ValueError):
+        it.interpolate(small, f, method="fast")
+
+
+def test_auto_keeps_the_exact_kernel_when_the_form_does_not_exist_or_fails_validation(monkeypatch):
+    rng = np.random.default_rng(7)
+    # knots that are not nested: no hierarchical form
+    it = SGInterpolant(mis.smolyak_mid_set(3, 4), nodes_1d.cc_nodes, lambda n: n + 1, verbose=False)
+    f = rng.normal(size=(it.num_nodes, 2))
+    x = rng.uniform(-1, 1, (20000, 4))
+    assert np.array_equal(it.interpolate(x, f), it.interpolate(x, f, method="combination"))
+    assert it.auto_validation["enabled"] is False
+    # other operators: never
+    from sgmethods_b200.tp_inteprolants import TPPwQuadraticInterpolator
+    itq = SGInterpolant(mis.smolyak_mid_set(2, 3), nodes_1d.cc_nodes,
+                        lambda n: np.where(n == 0, 1, 2 ** n + 1),
+                        tp_interpolant=TPPwQuadraticInterpolator, verbose=False)
+    fq = rng.normal(size=(itq.num_nodes, 1))
+    xq = rng.uniform(-1, 1, (20000, 3))
+    assert np.array_equal(itq.interpolate(xq, fq), itq.interpolate(xq, fq, method="combination"))
+    # a validation that fails (tolerance forced to 0) leaves the exact kernel in place
+    it2 = config2(2)
+    monkeypatch.setattr(sgi, "AUTO_TOL", 0.0)
+    f2 = rng.normal(size=(it2.num_nodes, 1))
+    x2 = rng.normal(size=(20000, 16))
+    out = it2.interpolate(x2, f2)
+    assert it2._auto_choice == "combination" and not it2.auto_validation["enabled"]
+    assert np.array_equal(out, it2.interpolate(x2, f2, method="combination"))
+
+
+def test_auto_pipelined_host_inputs_and_torch_tensors():
+    import torch
+    it = config2(2)
+    P = 4 * 113664 + 999                                  # takes the chunked copy/compute pipeline
+    x = np.random.default_rng(8).normal(size=(P, 18))     # 2 unused columns
+    f = np.random.default_rng(9).normal(size=(it.num_nodes, 1))
+    got = it.interpolate(x, f)
+    assert it._auto_choice == "hierarchical"
+    ref = it.interpolate(torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda(), method="hierarchical")
+    assert isinstance(got, np.ndarray) and np.array_equal(got, ref.cpu().numpy())
+    pinned = torch.from_numpy(x).pin_memory()
+    assert torch.equal(it.interpolate(pinned, torch.from_numpy(f)), ref)
+    exact = it.interpolate(torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda(), method="combination")
+    assert rel_dev(got, exact.cpu().numpy()) <= TOL
+
+
+def test_hierarchical_nan_and_ragged_batches():
+    it = config2(2)
+    rng = np.random.default_rng(10)
+    f = rng.normal(size=(it.num_nodes, 3))
+    for P in (1, 31, 33, 1000, 4097):
+        x = rng.normal(size=(P, 16))
+        if P > 1:
+            x[P // 2, 5] = np.nan
+        fast = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(P, 3)
+        exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(P, 3)
+        assert rel_dev(fast, exact) <= TOL

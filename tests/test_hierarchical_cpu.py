@@ -52,7 +52,13 @@ def emulate_groups(hp, x, f):
     T, N = tf.shape
     n_fam = len(hp.rank_knots) - 1
     extent = np.array([(hp._newrank[r] >= 0).sum() for r in range(1, n_fam + 1)], dtype=np.int32)
-    groups, parents, steps, hmap, root = _lib.hier_groups(tf, extent, hp._map_off[:T])
+    groups, parents, steps, hmap, root, split = _lib.hier_groups(tf, extent, hp._map_off[:T], 64)
+    assert split[0] == 0 and split[-1] == groups.shape[0] and np.all(np.diff(split) >= 0)
+    # summation order: every group names its list and its position in it; positions count up
+    # along the table (= execution) order, so a list's earlier groups are always taken earlier
+    lists, pos = (groups[:, 1] >> 24) & 0x3f, groups[:, 11]
+    for w in range(split.size - 1):
+        assert np.array_equal(pos[lists == w], np.arange(split[w + 1] - split[w]))
     # the kernel's own value table: a gather of the surpluses through hmap, zeros in the padding
     used = hmap[hmap >= 0]
     assert np.array_equal(np.sort(used), np.arange(hp._map_off[T]))      # every surplus exactly once
@@ -92,10 +98,10 @@ def emulate_groups(hp, x, f):
             if m < n_mem:
                 w.append(w_par * (phi[e] if e < len(ent) else 1.0))
                 off.append(off_par + gr[2] * (rank[e] if e < len(ent) else 0))
-        bounds = [int(b) for b in gr.view(np.uint16)[16:24]]
+        bounds = [int(b) for b in gr.view(np.uint16)[16:22]] + [n_steps]
         for si, (sbase, word) in enumerate(steps[gr[0]:gr[0] + n_steps]):
             e, slot = (int(word) & 0xffff) // 64, (int(word) & 0xffffffff) >> 16
-            nv = 7 - next(i for i in range(8) if si < bounds[i] or i == 7)      # member count class
+            nv = 7 - next(i for i in range(7) if si < bounds[i])               # member count class
             assert 1 <= nv <= n_mem
             for m in range(nv):
                 idx = sbase + m * slot + off[m] + gr[3] * rank[e]

@@ -42,8 +42,8 @@ def timed(label):
 os.environ["SGM_NO_H2"] = "1"
 timed("H1 (per multi-index)")
 del os.environ["SGM_NO_H2"]
-for shape, label in ((0, "16w x2 (64 regs)"), (1, "14w x2 (73 regs)"), (2, "12w x2 (85 regs)"),
-                     (3, "8w x3 (85 regs)"), (4, "16w x1 (128 regs)"), (5, "12w x2 unroll4")):
+for shape, label in ((0, "16w x2"), (1, "16w x2 contiguous tiles"), (2, "8w x4"),
+                     (3, "8w x3"), (4, "16w x1"), (5, "16w x2 unroll4")):
     os.environ["SGM_H2_SHAPE"] = str(shape)
     timed("H2 " + label)
 del os.environ["SGM_H2_SHAPE"]
