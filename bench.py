@@ -45,33 +45,55 @@ UNIT = "point-evals*outputs/s"
 
 
 # ------------------------------------------------------------------------------- workloads
+WORKLOADS = ("c1", "c2", "c2small", "c2leja", "c3", "c3full", "c4", "c5")
+
+
 def build_workload(name):
-    """Returns (interpolant, description, points-per-rank, NF, point sampler kind)."""
+    """Returns (interpolant, description, points-per-rank, NF, point sampler kind).  For "c4"
+    the first entry is an MLInterpolant (4 levels) -- see run_multilevel()."""
     from sgmethods_b200 import multi_index_sets as mis, nodes_1d
     from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
-    from sgmethods_b200.tp_inteprolants import TPLagrangeInterpolator
+    from sgmethods_b200.tp_inteprolants import TPLagrangeInterpolator, TPPwQuadraticInterpolator
+    l2 = lambda n: 2 ** (n + 1) - 1  # noqa: E731
     if name == "c2":
-        it = SGInterpolant(mis.smolyak_mid_set(4, 16), nodes_1d.unbounded_nodes_nested,
-                           lambda n: 2 ** (n + 1) - 1, verbose=False)
+        it = SGInterpolant(mis.smolyak_mid_set(4, 16), nodes_1d.unbounded_nodes_nested, l2, verbose=False)
         return it, "config2: d=16 smolyak(w=4) unbounded-nested knots pw-linear NF=1", 10 ** 6, 1, "normal"
     if name == "c2small":
-        it = SGInterpolant(mis.smolyak_mid_set(3, 16), nodes_1d.unbounded_nodes_nested,
-                           lambda n: 2 ** (n + 1) - 1, verbose=False)
+        it = SGInterpolant(mis.smolyak_mid_set(3, 16), nodes_1d.unbounded_nodes_nested, l2, verbose=False)
         return it, "config2-small: d=16 smolyak(w=3) pw-linear NF=1", 10 ** 5, 1, "normal"
+    if name == "c2leja":
+        # BASELINE config 2's wording: Gaussian weighted-Leja knots (the sequence the reference
+        # ships as .mat data; its first 12 points are a test fixture), Lagrange operator
+        from sgmethods_b200.leja import leja_knots
+        with np.load(os.path.join(ROOT, "tests", "golden", "lag_leja_gauss.npz")) as z:
+            knots = leja_knots(z["leja_X"])
+        it = SGInterpolant(mis.smolyak_mid_set(4, 16), knots, lambda nu: nu + 1,
+                           tp_interpolant=TPLagrangeInterpolator, verbose=False)
+        return it, "config2-leja: d=16 smolyak(w=4) Gaussian-Leja knots Lagrange NF=1", 10 ** 6, 1, "normal"
     if name == "c1":
         aniso = 2 ** (np.linspace(0, 7, 8))
         it = SGInterpolant(mis.aniso_smolyak_mid_set(4, 8, aniso), nodes_1d.cc_nodes,
                            lambda n: np.where(0, 1, 2 ** n + 1),
                            tp_interpolant=TPLagrangeInterpolator, verbose=False)
         return it, "config1: example/0 as shipped (Lagrange, d=8, 7 terms)", 256, 1, "uniform"
-    if name == "c3":
+    if name in ("c3", "c3full"):
         from sgmethods_b200.utils import compute_level_lc
         a = np.array([compute_level_lc(n)[0] + 1 for n in range(64)], dtype=float)
-        it = SGInterpolant(mis.aniso_smolyak_mid_set(8, 64, a),
-                           lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2),
-                           lambda n: 2 ** (n + 1) - 1, verbose=False)
-        return it, "config3 (w=8): LC anisotropy d=64 pw-linear NF=10^4", 10 ** 4, 10 ** 4, "normal"
-    raise SystemExit(f"unknown workload {name}")
+        w, P = (8, 10 ** 4) if name == "c3" else (10, 10 ** 5)
+        it = SGInterpolant(mis.aniso_smolyak_mid_set(w, 64, a),
+                           lambda n: nodes_1d.optimal_gaussian_nodes(n, p=2), l2, verbose=False)
+        return it, f"config3 (w={w}): LC anisotropy d=64 pw-linear NF=10^4, {P} points", P, 10 ** 4, "normal"
+    if name == "c4":
+        from sgmethods_b200.multilevel_interpolant import MLInterpolant
+        dbl = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa: E731
+        seq = [SGInterpolant(mis.smolyak_mid_set(k, 8), nodes_1d.cc_nodes, dbl,
+                             tp_interpolant=TPPwQuadraticInterpolator, verbose=False) for k in range(4)]
+        return MLInterpolant(seq), "config4: multilevel, 4 levels, pw-quadratic d=8 NF=10^3", 10 ** 6, 10 ** 3, "uniform"
+    if name == "c5":
+        S = mis.aniso_smolyak_mid_set(3, 128, np.array([1.0] * 80 + [3.0] * 48))
+        it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, l2, verbose=False)
+        return it, "config5: d=128, 91 929 terms, pw-linear NF=1", 10 ** 6, 1, "normal"
+    raise SystemExit(f"unknown workload {name} (choices: {', '.join(WORKLOADS)})")
 
 
 def algorithmic_bytes(it, P, NF):
@@ -160,6 +182,40 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------- CPU baseline
 _CPU_STATE = {}
+KIND_NAME = {0: "linear", 1: "quadratic", 2: "cubic", 3: "lagrange"}
+
+
+def reference_tables(name):
+    """Everything the CPU arm needs for a workload: the oracle's plan (per-term tables), N,
+    number of nodes, operator kind, NF, sampler, description.  From bench_data/<name>.npz
+    (tools/make_ref_tables.py) when it exists -- then neither this function nor the arm touches
+    the product library --, else built with the product's table builder."""
+    from oracle import sg_oracle
+    path = os.path.join(ROOT, "bench_data", name + ".npz")
+    if os.path.exists(path):
+        with np.load(path) as z:
+            g = {k: z[k] for k in z.files}
+        T = g["coeffs"].size
+        knots_of = {int(m): g["fam_knots"][g["fam_off"][i]:g["fam_off"][i + 1]]
+                    for i, m in enumerate(g["fam_m"])}
+        dims, nodes, maps = [], [], []
+        for t in range(T):
+            lo, hi = g["dims_off"][t], g["dims_off"][t + 1]
+            shape = tuple(int(v) for v in g["shapes"][lo:hi])
+            dims.append(g["dims"][lo:hi].astype(np.int64))
+            nodes.append(tuple(knots_of[m] for m in shape) if shape else (g["knots_one"],))
+            maps.append(g["maps"][g["map_off"][t]:g["map_off"][t + 1]].astype(np.int64)
+                        .reshape(shape or (1,)))
+        plan = sg_oracle.plan_from_tables(int(g["N"]), list(g["coeffs"]), dims, nodes, maps)
+        return dict(plan=plan, N=int(g["N"]), num_nodes=int(g["num_nodes"]), kind=KIND_NAME[int(g["kind"])],
+                    NF=int(g["NF"]), sampler=str(g["sampler"]), desc=str(g["desc"]), terms=T,
+                    tables="bench_data/%s.npz (tools/make_ref_tables.py)" % name)
+    it, desc, P, NF, sampler = build_workload(name)
+    plan = sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
+                                      it.active_tp_nodes_list, it.map_tp_to_SG)
+    return dict(plan=plan, N=it.N, num_nodes=it.num_nodes, kind=KIND_NAME[it._kind], NF=NF,
+                sampler=sampler, desc=desc, terms=len(it._coeffs),
+                tables="built by the product's table builder (no cache file for this workload)")
 
 
 def _cpu_worker(args):
@@ -170,48 +226,186 @@ def _cpu_worker(args):
                                  if st["kind"] == "linear" else st["kind"], squeeze=False)
 
 
-def cpu_reference_rate(it, kind, NF, sample_points, seed=0, sampler="normal", repeats=1):
+def cpu_reference_rate(ref, sample_points, seed=0, cores=None):
     """Throughput of the CPU oracle port on `sample_points` points of the workload, split
-    over all host cores (fork pool).  Returns (value, cores, seconds, sample description)."""
+    over `cores` processes (default: all host cores; fork pool).  Returns (value, cores,
+    seconds, sample description)."""
     import multiprocessing as mp
-    from oracle import sg_oracle
-    cores = os.cpu_count() or 1
+    cores = cores or os.cpu_count() or 1
     rng = np.random.default_rng(seed)
-    x = rng.normal(size=(sample_points, it.N)) if sampler == "normal" else \
-        rng.uniform(-1, 1, (sample_points, it.N))
-    f = np.random.default_rng(1).normal(size=(it.num_nodes, NF))
-    plan = sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
-                                      it.active_tp_nodes_list, it.map_tp_to_SG)
-    _CPU_STATE.update(plan=plan, x=x, f=f, kind=kind)
+    x = rng.normal(size=(sample_points, ref["N"])) if ref["sampler"] == "normal" else \
+        rng.uniform(-1, 1, (sample_points, ref["N"]))
+    f = np.random.default_rng(1).normal(size=(ref["num_nodes"], ref["NF"]))
+    _CPU_STATE.update(plan=ref["plan"], x=x, f=f, kind=ref["kind"])
+    if cores == 1:
+        t0 = time.perf_counter()
+        _cpu_worker((0, sample_points))
+        dt = time.perf_counter() - t0
+        return sample_points * ref["NF"] / dt, 1, dt, f"{sample_points} points, 1 process"
     bounds = np.linspace(0, sample_points, cores + 1).astype(int)
     chunks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
-    best = None
-    ctx = mp.get_context("fork")
-    with ctx.Pool(len(chunks)) as pool:
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, chunks)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return sample_points * NF / best, len(chunks), best, \
+    with mp.get_context("fork").Pool(len(chunks)) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, chunks)
+        dt = time.perf_counter() - t0
+    return sample_points * ref["NF"] / dt, len(chunks), dt, \
         f"{sample_points} points of the workload split over {len(chunks)} processes"
 
 
-def cpu_single_core_rate(it, kind, NF, sample_points, sampler="normal"):
-    from oracle import sg_oracle
-    rng = np.random.default_rng(0)
-    x = rng.normal(size=(sample_points, it.N)) if sampler == "normal" else \
-        rng.uniform(-1, 1, (sample_points, it.N))
-    f = np.random.default_rng(1).normal(size=(it.num_nodes, NF))
-    plan = sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
-                                      it.active_tp_nodes_list, it.map_tp_to_SG)
+# ------------------------------------------------------------------------------- GPU helpers
+def timed_steps(torch, fn, steps, flush, dist=None, dev=None):
+    """`steps` calls of fn, each bracketed by CUDA events on the current stream with the L2
+    flushed (256 MB fill) in between.  Returns the per-step milliseconds."""
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for s in range(steps):
+        flush.fill_(float(s))
+        starts[s].record()
+        fn()
+        ends[s].record()
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in zip(starts, ends)])
+
+
+def max_over_ranks(torch, dist, dev, value, world):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sample_points(torch, P, N, sampler, dev, gen):
+    if sampler == "normal":
+        return torch.randn((P, N), dtype=torch.float64, device=dev, generator=gen)
+    return torch.rand((P, N), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+
+
+def main_kernel_ms(plan, P):
+    """Mean duration of the sgm_eval launches of `plan` on P points recorded by its timing hook
+    (pre-gather + locality sort + evaluation kernel; the evaluation kernel is > 95 % of it,
+    profiles/r2_launches.csv)."""
+    ts = [a.elapsed_time(b) for (p, nf, a, b) in plan.timing if p == P]
+    return float(np.mean(ts)) if ts else None
+
+
+def run_extra(torch, name, dev, flush, peak, steps=2):
+    """One of the other BASELINE workloads at its named size on this GPU: throughput through
+    the public call on device-resident inputs + HBM roofline fraction of its algorithmic bytes."""
     t0 = time.perf_counter()
-    sg_oracle.interpolate(plan, x, f, "linear_scipy" if kind == "linear" else kind)
-    dt = time.perf_counter() - t0
-    return sample_points * NF / dt, dt
+    it, desc, P, NF, sampler = build_workload(name)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    if name == "c4":                                   # multilevel: 4 levels, one fused launch
+        mli, seq = it, it.interp_seq
+        yy = sample_points(torch, P, 8, sampler, dev, gen)
+        ml = [torch.randn((seq[3 - k].num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
+              for k in range(4)]
+        fn = lambda: mli.interpolate(yy, ml)            # noqa: E731
+        bytes_alg = 8 * P * 8 + 8 * P * NF + sum(8 * s.num_nodes * NF for s in seq) + \
+            sum(4 * s._maps.size for s in seq)
+        extra = {"levels": 4, "launches_per_step": 1, "terms": sum(len(s._coeffs) for s in seq[:1]) +
+                 sum(len(seq[k]._coeffs) + len(seq[k - 1]._coeffs) for k in range(1, 4))}
+    else:
+        x = sample_points(torch, P, it.N, sampler, dev, gen)
+        f = torch.randn((it.num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
+        fn = lambda: it.interpolate(x, f)               # noqa: E731
+        bytes_alg = algorithmic_bytes(it, P, NF)
+        extra = {"terms": len(it._coeffs), "nodes": it.num_nodes,
+                 "corners_per_point": it.device_plan(dev.index).corners_per_point}
+    build_s = time.perf_counter() - t0
+    fn()
+    ms = float(np.min(timed_steps(torch, fn, steps, flush)))
+    if name != "c4":
+        extra["method"] = getattr(it, "_auto_choice", None) or "combination"
+        extra["auto_validation"] = getattr(it, "auto_validation", None)
+        if extra["method"] == "hierarchical":           # the bit-exact path next to it
+            fx = lambda: it.interpolate(x, f, method="combination")   # noqa: E731
+            fx()
+            extra["exact_ms"] = float(np.min(timed_steps(torch, fx, steps, flush)))
+    out = {"workload": desc, "points": P, "NF": NF, "ms_per_step": ms, "value": P * NF / ms * 1e3,
+           "unit": UNIT, "algorithmic_bytes": bytes_alg, "hbm_gbs": bytes_alg / ms / 1e6,
+           "hbm_frac": bytes_alg / ms / 1e6 / peak, "host_setup_s": build_s, "timing": f"best of {steps}"}
+    out.update(extra)
+    return out
 
 
-KIND_NAME = {0: "linear", 1: "quadratic", 2: "cubic", 3: "lagrange"}
+def run_hbm_kernels(torch, dev, flush, peak, gen):
+    """The two HBM-bound kernels of the path family next to the gather-bound headline."""
+    from sgmethods_b200 import multi_index_sets as mis, nodes_1d
+    from sgmethods_b200.parametric_expansions_brownian_motion import lc_brownian_device
+    from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
+    res = {}
+    # (1) batched Levy-Ciesielski map of config 3's parameter vectors (SURVEY 8 row a13)
+    Pl, dl, ntl = 10 ** 5, 64, 10 ** 3
+    yy = torch.randn((Pl, dl), dtype=torch.float64, device=dev, generator=gen)
+    tt = torch.linspace(0, 1, ntl, dtype=torch.float64, device=dev)
+    Wl = torch.empty((Pl, ntl), dtype=torch.float64, device=dev)
+    fn = lambda: lc_brownian_device(tt, yy, 1.0, Wl)    # noqa: E731
+    for _ in range(3):
+        fn()
+    lms = float(np.median(timed_steps(torch, fn, 7, flush)))
+    lbytes = 8 * Pl * dl + 8 * ntl + 8 * Pl * ntl
+    res["hbm_bound_kernel"] = {
+        "kernel": "sgm::lc_brownian_tiles_kernel (Levy-Ciesielski expansion, d=64, 10^5 "
+                  "parameter vectors x 10^3 times)",
+        "ms": lms, "algorithmic_bytes": lbytes, "achieved": lbytes / lms / 1e6, "peak": peak,
+        "unit": "GB/s", "frac": lbytes / lms / 1e6 / peak}
+    # (2) the interpolant itself in its HBM-bound regime: example/1 as shipped (7 terms, 22
+    # corners per point), 10^7 points -- bit-identical to the reference
+    S = mis.aniso_smolyak_mid_set(5, 10, 2 ** (np.linspace(0, 9, 10)))
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+    P = 10 ** 7
+    x = torch.randn((P, it.N), dtype=torch.float64, device=dev, generator=gen)
+    f = torch.randn((it.num_nodes, 1), dtype=torch.float64, device=dev, generator=gen)
+    plan = it.device_plan(dev.index)
+    out = torch.empty((P, 1), dtype=torch.float64, device=dev)
+    fn = lambda: plan.eval(x, f, out)                   # noqa: E731
+    for _ in range(3):
+        fn()
+    ems = float(np.median(timed_steps(torch, fn, 7, flush)))
+    ebytes = algorithmic_bytes(it, P, 1)
+    res["hbm_bound_interpolant"] = {
+        "workload": "example/1 as shipped (pw-linear, d=10, 7 terms, 22 corners/point), 10^7 points, "
+                    "exact combination formula",
+        "ms": ems, "algorithmic_bytes": ebytes, "achieved": ebytes / ems / 1e6, "peak": peak,
+        "unit": "GB/s", "frac": ebytes / ems / 1e6 / peak, "value": P / ems * 1e3}
+    return res
+
+
+def run_indicators(torch, dev):
+    """Batched Gerstner-Griebel indicators (compute_GG_indicators_RM): all reduced-margin
+    candidates of an adaptive state in one segmented launch; candidates per second."""
+    from sgmethods_b200 import nodes_1d
+    from sgmethods_b200.compute_error_indicators import MeanSquareNorm, compute_GG_indicators_RM
+    from sgmethods_b200.mid_set import MidSet
+    from sgmethods_b200.sparse_grid_interpolant import SGInterpolant
+    ms = MidSet(track_reduced_margin=True)
+    rng = np.random.default_rng(11)
+    ms.enlarge_from_margin(0)
+    for step in range(60):                               # a 6-dimensional adaptive state
+        if ms.get_dim() < 6 and step % 4 == 0:
+            ms.increase_dim()
+        else:
+            ms.enlarge_from_margin(int(rng.integers(0, ms.get_cardinality_reduced_margin())))
+    knots, lev = nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1   # noqa: E731
+    f = lambda y: np.array([np.exp(-0.3 * np.sum(y * y)), np.sum(y)])         # noqa: E731
+    cur = SGInterpolant(ms.mid_set, knots, lev, verbose=False)
+    u_on_SG = cur.sample_on_SG(f)
+    yy = rng.normal(size=(20000, ms.get_dim()))
+    u_interp = cur.interpolate(yy, u_on_SG)
+    empty = (np.zeros((0, 0), dtype=int), np.zeros(0))
+    res = {}
+    for label, norm in (("gpu_norm", MeanSquareNorm()), ("host_norm_callback", lambda a, b: MeanSquareNorm()(a, b))):
+        compute_GG_indicators_RM(*empty, ms, knots, lev, f, cur.SG, u_on_SG, yy, norm, u_interp)
+        t0 = time.perf_counter()
+        est = compute_GG_indicators_RM(*empty, ms, knots, lev, f, cur.SG, u_on_SG, yy, norm, u_interp)
+        dt = time.perf_counter() - t0
+        res[label] = {"candidates": int(est.size), "seconds": dt, "candidates_per_s": est.size / dt}
+    res["state"] = {"dim": ms.get_dim(), "multi_indices": int(ms.get_cardinality_mid_set()),
+                    "reduced_margin": int(ms.get_cardinality_reduced_margin()), "random_points": 20000,
+                    "note": "wall clock of compute_GG_indicators_RM incl. host table building and "
+                            "sampling f on the new nodes; one segmented launch for all candidates"}
+    return res
 
 
 # ------------------------------------------------------------------------------- main
@@ -221,12 +415,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c2", choices=WORKLOADS)
     ap.add_argument("--points", type=int, default=0, help="points per rank (0 = workload default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-hierarchical", action="store_true",
-                    help="skip the extra (non-headline) measurement of the opt-in hierarchical form")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra keys (other workloads, HBM-bound kernels, indicators, scaling modes)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,32 +439,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        it, desc, P, NF, sampler = build_workload(args.workload)
-        kind = KIND_NAME[it._kind]
+        ref = reference_tables(args.workload)
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or cores * 1024
-        vals = []
-        for _ in range(max(args.warmup, 0) and 1):
-            cpu_reference_rate(it, kind, NF, max(cores * 64, 64), sampler=sampler)
-        t_all = time.perf_counter()
-        for s in range(args.steps):
-            v, used, dt, what = cpu_reference_rate(it, kind, NF, sample, seed=s, sampler=sampler)
-            vals.append((v, dt))
-        total = time.perf_counter() - t_all
-        value = sample * NF * len(vals) / sum(dt for _, dt in vals)
+        if args.warmup > 0:
+            cpu_reference_rate(ref, max(cores * 64, 64))
+        runs = [cpu_reference_rate(ref, sample, seed=s) for s in range(args.steps)]
+        total = sum(r[2] for r in runs)
+        value = sample * ref["NF"] * len(runs) / total
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals),
+                "ms_per_step": 1e3 * total / len(runs),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "points_per_step": sample, "NF": NF,
-                           "terms": len(it._coeffs), "nodes": it.num_nodes},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                                 "sample": what + "; oracle/ numpy+scipy port of the reference's "
-                                 "term loop, tables from the verified builder"},
+                "config": {"workload": ref["desc"], "points_per_step": sample, "NF": ref["NF"],
+                           "terms": ref["terms"], "nodes": ref["num_nodes"], "tables": ref["tables"]},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": runs[0][1], "kind": "port",
+                                 "sample": runs[0][3] + "; oracle/ numpy+scipy port of the reference's "
+                                 "term loop (bit-equal to the reference and of the same cost)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
-                "wall_s": total}
+                "native_library_loaded": "sgmethods_b200._lib" in sys.modules}
         print(json.dumps(line), file=json_out, flush=True)
         return 0
 
@@ -283,59 +472,84 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = measured_peak_gbs()
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    warmup = max(args.warmup, 3)
+
+    if args.workload == "c4":            # multilevel driver: its own (simpler) line
+        res = run_extra(torch, "c4", dev, flush, peak, steps=max(2, min(args.steps, 3)))
+        if rank == 0:
+            line = {"metric": METRIC, "value": world * res["value"], "unit": UNIT, "n_gpus": world,
+                    "steps": args.steps, "warmup": warmup, "ms_per_step": res["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic", "config": {"workload": res["workload"]}, "detail": res,
+                    "gpu_launches": 1}
+            print(json.dumps(line), file=json_out, flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     it, desc, P_default, NF, sampler = build_workload(args.workload)
     P = args.points or P_default
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    if sampler == "normal":
-        x = torch.randn((P, it.N), dtype=torch.float64, device=dev, generator=gen)
-    else:
-        x = torch.rand((P, it.N), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    x = sample_points(torch, P, it.N, sampler, dev, gen)
     f = torch.from_numpy(np.random.default_rng(1).normal(size=(it.num_nodes, NF))).to(dev)
-    plan = it.device_plan(local_rank)
-    out = torch.empty((P, NF), dtype=torch.float64, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    exact_plan = it.device_plan(local_rank)
+
+    # ---- the step: the public call on device-resident inputs, contract path (method="auto":
+    # hierarchisation of the nodal values, per-call validation, locality sort, evaluation)
+    out_holder = {}
 
     def step():
-        plan.eval(x, f, out)
+        out_holder["out"] = it.interpolate(x, f)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-
-    # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed between
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    method = getattr(it, "_auto_choice", None) or "combination"
+    main_plan = it.hierarchical()._dev(local_rank)[0] if method == "hierarchical" else exact_plan
+    main_plan.timing = []
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
     with ClockSampler(local_rank) as clocks:
         t_wall = time.perf_counter()
-        for s in range(args.steps):
-            flush.fill_(float(s))
-            starts[s].record()
-            step()
-            ends[s].record()
-        torch.cuda.synchronize()
+        step_ms = timed_steps(torch, step, args.steps, flush)
         wall = time.perf_counter() - t_wall
     if world > 1:
         dist.barrier()
-    step_ms = np.array([a.elapsed_time(b) for a, b in zip(starts, ends)])
-    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    kernel_ms = main_kernel_ms(main_plan, P)
+    main_plan.timing = None
+    total_ms = max_over_ranks(torch, dist, dev, step_ms.sum(), world)
     value = world * P * NF * args.steps / (total_ms * 1e-3)
+    out = out_holder["out"].reshape(P, NF).clone()
 
-    # ---- end to end through the public API with pinned host buffers
+    # ---- the bit-exact combination formula on the same batch (extra key, not the headline
+    # when the validated work-reduced form is in use)
+    exact_steps = max(3, min(args.steps, 5))
+    exact_out = torch.empty((P, NF), dtype=torch.float64, device=dev)
+    exact_plan.eval(x, f, exact_out)
+    exact_plan.timing = []
+    exact_ms = timed_steps(torch, lambda: exact_plan.eval(x, f, exact_out), exact_steps, flush)
+    exact_plan.timing = None
+    dev_rel = float((out - exact_out).abs().max() / exact_out.abs().max())
+
+    # ---- end to end through the public API with pinned host buffers; with several ranks the
+    # final NCCL all-gather of the (P, NF) slabs is part of it (north star item 4)
     x_host = x.cpu().pin_memory()
     f_host = f.cpu().pin_memory()
-    out_host = torch.empty((P, NF), dtype=torch.float64).pin_memory()
+    out_host = torch.empty((world * P, NF), dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
+    sh = None
+    if world > 1:
+        from sgmethods_b200.distributed import ShardedInterpolant
+        sh = ShardedInterpolant(it, mode="points")
 
     def e2e_step():
-        res = it.interpolate(x_host, f_host)          # H2D + kernel, returns a CUDA tensor
-        out_host.copy_(res.reshape(P, NF), non_blocking=True)   # D2H of the result
+        res = it.interpolate(x_host, f_host).reshape(P, NF)      # H2D + kernels, CUDA tensor
+        if sh is not None:
+            res = sh.gather_blocks(res, world * P, "all")        # NCCL all-gather of the slabs
+        out_host.copy_(res, non_blocking=True)                   # D2H of the (gathered) result
     e2e_step()
     torch.cuda.synchronize()
     if world > 1:
@@ -346,27 +560,24 @@ def main():
         e2e_step()
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * P * NF * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    # the drop-in call exactly as a reference user makes it: numpy in, numpy out (pageable
-    # host memory, staged through pinned buffers by the library); wall clock, rank-local
-    x_np, f_np = x_host.numpy(), f_host.numpy()
-    it.interpolate(x_np, f_np)
-    t_np = time.perf_counter()
-    for _ in range(3):
-        res_np = it.interpolate(x_np, f_np)
-    numpy_ms = (time.perf_counter() - t_np) / 3 * 1e3
-    assert np.array_equal(res_np.reshape(P, NF), out_host.numpy())
-    assert torch.equal(out_host.to(dev), out), "e2e result differs from the device-resident run"
+    e2e_ms = max_over_ranks(torch, dist, dev, e0.elapsed_time(e1), world)
+    e2e_value = world * P * NF * e2e_steps / (e2e_ms * 1e-3)
+    assert torch.equal(out_host[rank * P:(rank + 1) * P].to(dev), out), \
+        "e2e result differs from the device-resident run"
+    numpy_ms = None
+    if world == 1:
+        # the drop-in call exactly as a reference user makes it: numpy in, numpy out (pageable
+        # host memory, staged through pinned buffers by the library); wall clock
+        x_np, f_np = x_host.numpy(), f_host.numpy()
+        it.interpolate(x_np, f_np)
+        t_np = time.perf_counter()
+        for _ in range(3):
+            res_np = it.interpolate(x_np, f_np)
+        numpy_ms = (time.perf_counter() - t_np) / 3 * 1e3
+        assert np.array_equal(res_np.reshape(P, NF), out_host[:P].numpy())
 
     gather_ms = None
     if world > 1:
-        # the optional final exchange of the point-sharded result (north star item 4): NCCL
-        # all-gather of the (P, NF) slabs, timed separately from the collective-free step
-        from sgmethods_b200.distributed import ShardedInterpolant
-        sh = ShardedInterpolant(it, mode="points")
         sh.gather_blocks(out, world * P, "all")
         torch.cuda.synchronize()
         dist.barrier()
@@ -376,115 +587,101 @@ def main():
             full = sh.gather_blocks(out, world * P, "all")
         g1.record()
         torch.cuda.synchronize()
-        gm = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
-        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
-        gather_ms = float(gm.item())
+        gather_ms = max_over_ranks(torch, dist, dev, g0.elapsed_time(g1) / 5, world)
         assert full.shape == (world * P, NF)
 
+    scaling_extras = {}
+    if not args.no_extras and args.workload == "c2":
+        scaling_extras = run_scaling_modes(torch, dist, dev, rank, world, flush)
+
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        kernel_ms = float(np.mean(step_ms))
+        clk = clocks.summary()
+        kernel_ms = kernel_ms if kernel_ms is not None else float(np.mean(step_ms))
         bytes_alg = algorithmic_bytes(it, P, NF)
         achieved = bytes_alg / (kernel_ms * 1e-3) / 1e9
-        corners = plan.corners_per_point
+        corners = exact_plan.corners_per_point
+        hier = method == "hierarchical"
+        gathers = it.hierarchical()._term_fam.shape[0] if hier else corners
+        exact_kernel_ms = main_kernel_ms_list(exact_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "warmup": warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": desc, "points_per_gpu": P, "NF": NF, "N": it.N,
                        "terms": len(it._coeffs), "nodes": it.num_nodes,
                        "corners_per_point": corners, "l2": "flushed between timed steps "
-                       "(256 MB fill)", "sharding": "points, no collective"},
-            "gpu_launches": 5 * args.steps,   # pregather, sort hist/scan/scatter, eval
+                       "(256 MB fill)", "sharding": "points (weak scaling: every rank its own batch); "
+                       "no data-path collective in the step, final NCCL all-gather inside e2e",
+                       "step": "SGInterpolant.interpolate(x, f) on device-resident tensors, method='auto'",
+                       "method_in_use": method, "auto_validation": getattr(it, "auto_validation", None),
+                       "max_rel_deviation_from_exact_combination_formula": dev_rel},
+            # per step: hier_apply_all, validation (2 x pregather + eval), pregather, sort
+            # hist/scan/scatter, evaluation kernel -- or pregather, sort x3, eval on the exact path
+            "gpu_launches": (10 if hier else 5) * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
-                    "d2h_bytes_per_step": int(P * NF * 8), "steps": e2e_steps,
-                    "numpy_in_numpy_out": {"value": P * NF / (numpy_ms * 1e-3), "ms_per_call": numpy_ms,
-                                           "note": "SGInterpolant.interpolate(ndarray, ndarray) -> "
-                                                   "ndarray on rank 0, pageable memory, wall clock"}},
+                    "d2h_bytes_per_step": int(world * P * NF * 8), "steps": e2e_steps,
+                    "includes_final_all_gather": world > 1},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P)),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the "
-                         "kernel, ncu --set full capture of this command "
-                         "(profiles/r1_v5_prefix_ppl2_ncu_full.txt)",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_alg,
-                         "kernel": "sgm::eval_points_prefix_kernel<8 warps, 64-term chunks, balanced "
-                                   "runs, 2 points per lane> (+ pregather and the point locality "
-                                   "sort, <1% of the step; profiles/r1_v5_launches.csv)",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P, method)),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the kernel, "
+                                           "ncu --set full capture of this command (profiles/)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
+                         "kernel": ("sgm::eval_hier_groups_kernel<16 warps, 2 blocks/SM> (grouped "
+                                    "hierarchical-surplus kernel)" if hier else
+                                    "sgm::eval_points_prefix_kernel / split kernel (exact combination formula)")
+                                   + " + pre-gather and point locality sort (< 5 % of the launch group)",
                          "kernel_ms": kernel_ms,
-                         "note": "the exact combination form is bound by the SM's L1 data pipe "
-                                 "(128 B/clk/SM; 8-byte corner gathers + bracket tables) and "
-                                 "FP64 issue, not HBM (DESIGN.md section 5); ncu of this kernel: "
-                                 "L1 data pipe 68 %, issue 46 %, FP64 pipe 38 % of peak "
-                                 "(profiles/r1_v5_prefix_ppl2_ncu_full.txt)",
-                         "corner_gathers_per_s": P * corners / (kernel_ms * 1e-3),
-                         "secondary": secondary_rooflines(P, corners, len(it._coeffs),
-                                                          kernel_ms, clocks.summary())},
-            "clocks": clocks.summary(),
+                         "note": "gather-bound, not HBM-bound: per point " + str(gathers) +
+                                 (" surplus gathers (one per multi-index)" if hier else " corner gathers") +
+                                 " of 8 bytes from an L1/L2-resident table against "
+                                 f"{bytes_alg / P:.0f} algorithmic HBM bytes (DESIGN.md section 5)",
+                         "gathers_per_s": P * gathers / (kernel_ms * 1e-3),
+                         "secondary": {"l1_data_pipe_floor_ms": P * gathers * 16 / (128 * 148 * 1.965e9) * 1e3
+                                       if hier else secondary_rooflines(P, corners, 0, kernel_ms, clk)["l1_data_pipe_floor_ms"],
+                                       "note": "L1 data pipe 128 B/clk/SM; a warp-wide 64-bit gather "
+                                               "needs >= 2 wavefronts"}},
+            "exact_mode": {"value": P * NF / (float(np.mean(exact_ms)) * 1e-3), "unit": UNIT,
+                           "ms_per_step": float(np.mean(exact_ms)), "steps": exact_steps,
+                           "hbm_frac": bytes_alg / (float(np.mean(exact_ms)) * 1e-3) / 1e9 / peak,
+                           "corner_gathers_per_s": P * corners / (float(np.mean(exact_ms)) * 1e-3),
+                           "note": "method='combination': the reference's formula bit for bit "
+                                   "(sgm_eval on the same batch)"},
+            "clocks": clk,
             "wall_s_timed_region": wall,
         }
-        if world == 1 and not args.no_hierarchical and it._kind == 0:
-            # extra, NOT the headline: the opt-in hierarchical-surplus form of the same
-            # interpolant (same function, not bit-identical)
-            try:
-                hp = it.hierarchical()
-                hv = hp.interpolate(x, f)
-                dev_rel = float((hv.reshape(out.shape) - out).abs().max() / out.abs().max())
-                hs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-                torch.cuda.synchronize()
-                for i in range(5):
-                    flush.fill_(0.0)
-                    hs[0].record(); hp.interpolate(x, f); hs[1].record()
-                    torch.cuda.synchronize()
-                    hms = hs[0].elapsed_time(hs[1]) if i == 0 else min(hms, hs[0].elapsed_time(hs[1]))
-                line["hierarchical_mode"] = {
-                    "value": P * NF / (hms * 1e-3), "unit": UNIT, "ms_per_step": hms,
-                    "max_rel_deviation_from_headline_result": dev_rel,
-                    "note": "opt-in method='hierarchical' (surplus form, ~10x fewer gathers); "
-                            "includes the GPU hierarchisation of the nodal values; best of 5"}
-            except NotImplementedError as exc:
-                line["hierarchical_mode"] = {"unavailable": str(exc)}
-        if world == 1:
-            # the HBM-bound kernel of the same path family: batched
-            # Levy-Ciesielski map of config 3's parameter vectors, bytes = 8 P d + 8 nt + 8 P nt
-            from sgmethods_b200.parametric_expansions_brownian_motion import lc_brownian_device
-            Pl, dl, ntl = 10 ** 5, 64, 10 ** 3
-            yy = torch.randn((Pl, dl), dtype=torch.float64, device=dev, generator=gen)
-            tt = torch.linspace(0, 1, ntl, dtype=torch.float64, device=dev)
-            Wl = torch.empty((Pl, ntl), dtype=torch.float64, device=dev)
-            for _ in range(3):
-                lc_brownian_device(tt, yy, 1.0, Wl)
-            lts = []
-            for i in range(7):
-                flush.fill_(float(i))
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); lc_brownian_device(tt, yy, 1.0, Wl); b.record()
-                torch.cuda.synchronize()
-                lts.append(a.elapsed_time(b))
-            lms = float(np.median(lts))
-            lbytes = 8 * Pl * dl + 8 * ntl + 8 * Pl * ntl
-            line["hbm_bound_kernel"] = {
-                "kernel": "sgm::lc_brownian_tiles_kernel (Levy-Ciesielski expansion, d=64, 10^5 "
-                          "parameter vectors x 10^3 times)",
-                "ms": lms, "algorithmic_bytes": lbytes, "achieved": lbytes / lms / 1e6, "peak": peak,
-                "unit": "GB/s", "frac": lbytes / lms / 1e6 / peak,
-                "note": "not the headline workload: shows the HBM fraction of the path's "
-                        "HBM-bound kernel next to the gather-bound evaluation kernel"}
+        if numpy_ms is not None:
+            line["e2e"]["numpy_in_numpy_out"] = {
+                "value": P * NF / (numpy_ms * 1e-3), "ms_per_call": numpy_ms,
+                "note": "SGInterpolant.interpolate(ndarray, ndarray) -> ndarray, pageable memory, wall clock"}
         if gather_ms is not None:
             line["final_all_gather"] = {"ms": gather_ms, "bytes_per_rank": int(P * NF * 8),
                                         "backend": "nccl all_gather_into_tensor",
-                                        "in_timed_step": False}
+                                        "note": "timed alone; it is also inside every e2e step"}
+        line.update(scaling_extras)
+        if world == 1 and not args.no_extras and args.workload == "c2":
+            line.update(run_hbm_kernels(torch, dev, flush, peak, gen))
+            line["extra_workloads"] = {}
+            for name in ("c2leja", "c5", "c3full", "c4"):
+                try:
+                    line["extra_workloads"][name] = run_extra(torch, name, dev, flush, peak)
+                except Exception as exc:                 # keep the headline line whatever happens
+                    line["extra_workloads"][name] = {"error": repr(exc)}
+                torch.cuda.empty_cache()
+            try:
+                line["error_indicators"] = run_indicators(torch, dev)
+            except Exception as exc:
+                line["error_indicators"] = {"error": repr(exc)}
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
+            ref = reference_tables(args.workload)
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or cores * 1024
-            v, used, dt, what = cpu_reference_rate(it, KIND_NAME[it._kind], NF, sample,
-                                                   sampler=sampler)
+            v, used, dt, what = cpu_reference_rate(ref, sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                                     "sample": what + f" ({dt:.1f} s)"}
             # the reference as shipped is single-threaded: the same port on ONE core
-            v1, dt1 = cpu_single_core_rate(it, KIND_NAME[it._kind], NF, 1024, sampler)
+            v1, _, dt1, _ = cpu_reference_rate(ref, 1024, cores=1)
             line["cpu_baseline"]["single_core"] = {"value": v1, "cores": 1,
                                                    "sample": f"1024 points, 1 process ({dt1:.1f} s)"}
         print(json.dumps(line), file=json_out, flush=True)
@@ -492,6 +689,94 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def main_kernel_ms_list(ms):
+    return float(np.mean(ms))
+
+
+def run_scaling_modes(torch, dist, dev, rank, world, flush):
+    """Two extra measurements that say something about multi-GPU behaviour (also run at N = 1 so
+    that the N > 1 lines have their baseline):
+      strong_scaling_c5  config 5 (d=128, 91 929 terms), a FIXED 4x10^6-point batch split over
+                         the ranks, result gathered to rank 0 (NCCL gather), exact kernel;
+      terms_mode_c5      the same interpolant at 4096 points with the TERMS sharded over the ranks
+                         and an NCCL all-reduce of the partial sums; deviation from the
+                         single-GPU result reported."""
+    from sgmethods_b200.distributed import ShardedInterpolant, shard_bounds
+    it, desc, _, NF, sampler = build_workload("c5")
+    f = torch.from_numpy(np.random.default_rng(1).normal(size=(it.num_nodes, 1))).to(dev)
+    res = {}
+    # ---- strong scaling: fixed total batch, every rank generates the SAME full point set from
+    # one seed and evaluates its block (method='combination' so that ranks and N agree bit for bit)
+    P_total = 4 * 10 ** 6
+    b = shard_bounds(P_total, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    g = torch.Generator(device=dev).manual_seed(4242)
+    CH = 10 ** 6
+    xs = []
+    for c0 in range(0, P_total, CH):                       # same stream of random numbers on all ranks
+        blk = torch.randn((min(CH, P_total - c0), it.N), dtype=torch.float64, device=dev, generator=g)
+        a, e = max(lo, c0), min(hi, c0 + blk.shape[0])
+        if e > a:
+            xs.append(blk[a - c0:e - c0].clone())
+        del blk
+    x_loc = torch.cat(xs) if xs else torch.empty((0, it.N), dtype=torch.float64, device=dev)
+    sh = ShardedInterpolant(it, mode="points")
+    plan = it.device_plan(dev.index)
+    plan.eval(x_loc[:4096], f)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    loc = plan.eval(x_loc, f)
+    e1.record()
+    full = sh.gather_blocks(loc, P_total, "root")
+    e2.record()
+    torch.cuda.synchronize()
+    t_eval = max_over_ranks(torch, dist, dev, e0.elapsed_time(e1), world)
+    t_all = max_over_ranks(torch, dist, dev, e0.elapsed_time(e2), world)
+    checksum = float(full.sum().item()) if rank == 0 else 0.0
+    res["strong_scaling_c5"] = {
+        "workload": desc, "points_total": P_total, "n_gpus": world, "scaling": "strong",
+        "eval_ms": t_eval, "eval_plus_gather_to_rank0_ms": t_all, "gather_ms": t_all - t_eval,
+        "value": P_total / (t_all * 1e-3), "unit": UNIT, "checksum": checksum,
+        "limits": "evaluation kernel (the gather of 8 B per point is < 1 % of the step)"}
+    # ---- term sharding: few points, huge term set
+    P_small = 4096
+    x_small = torch.randn((P_small, it.N), dtype=torch.float64, device=dev,
+                          generator=torch.Generator(device=dev).manual_seed(99))
+    single = plan.eval(x_small, f)
+    st = ShardedInterpolant(it, mode="terms")
+    st.interpolate(x_small, f)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        part = st.interpolate(x_small, f)
+    t1.record()
+    torch.cuda.synchronize()
+    t_terms = max_over_ranks(torch, dist, dev, t0.elapsed_time(t1) / 3, world)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(3):
+        plan.eval(x_small, f)
+    s1.record()
+    torch.cuda.synchronize()
+    t_single = max_over_ranks(torch, dist, dev, s0.elapsed_time(s1) / 3, world)
+    dev_rel = float((part - single).abs().max() / single.abs().max())
+    res["terms_mode_c5"] = {
+        "workload": desc, "points": P_small, "n_gpus": world, "terms_per_rank": int(len(it._coeffs) // world),
+        "ms_terms_sharded_incl_allreduce": t_terms, "ms_single_gpu_all_terms": t_single,
+        "speedup": t_single / t_terms, "max_rel_deviation_from_single_gpu": dev_rel,
+        "collective": "nccl all_reduce (sum, fp64) of the (P, NF) partial sums" if world > 1 else "none (1 rank)",
+        "limits": "evaluation kernel per rank; the all-reduce moves 32 KB"}
+    del x_loc, loc, full
+    torch.cuda.empty_cache()
+    return res
 
 
 if __name__ == "__main__":

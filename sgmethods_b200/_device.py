@@ -84,6 +84,9 @@ class DevicePlan:
         self.table_bytes = int(lib.sgm_plan_table_bytes(handle))
         self.corners_per_point = int(lib.sgm_plan_corners_per_point(handle))
         self._workspaces = {}
+        # measurement hook (bench.py): a list to which every eval appends (P, NF, start, end)
+        # CUDA events recorded around the sgm_eval launches on the launching stream
+        self.timing = None
         _LIVE_PLANS.add(self)
 
     # -- evaluation -------------------------------------------------------------------------
@@ -113,11 +116,17 @@ class DevicePlan:
         assert (x.shape[1] == 1 or x.stride(1) == 1) and (NF == 1 or f.stride(1) == 1)
         ws = self.workspace(P, NF)
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        if self.timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(torch.cuda.current_stream(x.device))
         _lib.check(_lib.load().sgm_eval(
             self._h, x.data_ptr(), P, x.stride(0) if P > 1 else max(x.shape[1], 1),
             f.data_ptr(), f.shape[0], NF, f.stride(0) if f.shape[0] > 1 else max(NF, 1),
             out.data_ptr(), out.stride(0) if P > 1 else max(NF, 1), ws.data_ptr(), ws.numel(),
             stream))
+        if self.timing is not None:
+            t1.record(torch.cuda.current_stream(x.device))
+            self.timing.append((P, NF, t0, t1))
         return out
 
     def _check_inputs(self, x, f):

@@ -63,3 +63,20 @@ def test_match_rows_semantics():
     # values chained closer than the tolerance: falls back to the exact all-pairs search
     chain = np.array([[0.0], [6e-11], [1.2e-10], [1.8e-10]])
     assert _lib.match_rows(np.array([[1.8e-10 + 9e-11]]), chain).tolist() == [3]
+
+
+def test_reference_arm_of_the_bench_is_numpy_scipy_only():
+    """`bench.py --impl reference` (the CPU baseline the driver runs) takes its tables from
+    bench_data/c2.npz and never loads the product's native library."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0", "--cpu-sample", "32"], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["native_library_loaded"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
