@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -58,7 +59,7 @@ struct Knobs {
     int prefix_run = 8;          // SGM_PREFIX_RUN
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
-    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false;
+    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false;
     int wide_pairs = -1;         // SGM_WIDE_PAIRS: -1 = automatic, 0 | 1
     long long col_loop_max = -1; // SGM_COL_LOOP_MAX
     int h2_shape = 0;            // SGM_H2_SHAPE: first launch shape of the grouped hierarchical kernel
@@ -74,6 +75,7 @@ struct Knobs {
         k.no_idx8 = std::getenv("SGM_NO_IDX8") != nullptr;
         k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
+        k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
         if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
         if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
         if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 6;
@@ -94,6 +96,10 @@ struct sgm_plan {
     int prefix_wins = 0;         // occupancy comparison prefix vs split kernel (plan creation)
     bool prefix_launch_ok = false;
     bool h2_ok = false;          // tables of the grouped hierarchical kernel are built
+    bool small_ok = false;       // kernel A0: few pw-linear terms, metadata in kernel parameters
+    sgm::SmallPlan small{};
+    const double* small_knots = nullptr;       // knots re-ordered for kernel A0 (device)
+    const unsigned short* small_tabs = nullptr;
     int64_t table_bytes = 0;
     int kmax = 0;
     int max_entry_n = 0;         // largest knot family among the table entries
@@ -332,6 +338,29 @@ void decide_prefix(sgm_plan* plan) {
     const SplitLaunch S = choose_split_launch<SGM_PW_LINEAR>(plan);
     plan->prefix_launch_ok = L.warps > 0;
     plan->prefix_wins = L.warps > 0 && 4 * L.warps * L.blocks_per_sm >= 3 * S.warps * S.blocks_per_sm;
+}
+
+// Kernel A0: few packed pw-linear terms, many points (gathers its node values itself).
+bool use_small_kernel(const sgm_plan* plan, int64_t P) {
+    return plan->small_ok && !plan->knobs.no_small && !plan->knobs.force_kernel && P >= 16384;
+}
+int launch_points_small(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                        int64_t ldf, double* out, int64_t ldo, double scale, int accumulate,
+                        cudaStream_t stream) {
+    constexpr int TH = 128, PPT = 2;
+    const sgm::SmallPlan& sp = plan->small;
+    const size_t smem = (size_t)sp.n_knots * 8 + (size_t)sp.E * TH * PPT * 10 + (size_t)plan->n_vals * 8 +
+                        (size_t)sp.n_tab * 2 + 16;
+    auto kern = sgm::eval_points_small_kernel<TH, PPT>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    SGM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, smem));
+    if (bps < 1) return sgm_fail(SGM_ERR_OVERFLOW, "small-plan kernel does not fit");
+    const int64_t nb = std::min<int64_t>((P + TH * PPT - 1) / (TH * PPT), (int64_t)plan->sm_count * bps * 2);
+    kern<<<(unsigned)nb, TH, smem, stream>>>(sp, plan->small_knots, plan->small_tabs, x, P, ldx, plan->dev.maps,
+                                            (int)plan->n_vals, f, ldf, out, ldo, scale, accumulate);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
 }
 
 int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
@@ -609,6 +638,8 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         const size_t g_bytes = g_bytes_of(plan);
         if (workspace_bytes < g_bytes || !workspace)
             return sgm_fail(SGM_ERR_WORKSPACE, "eval: workspace too small");
+        if (kind == SGM_PW_LINEAR && use_small_kernel(plan, P))
+            return launch_points_small(plan, x, P, ldx, f + col, ldf, out + col, ldo, scale, accumulate, stream);
         double* G = static_cast<double*>(workspace);
         unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
         const bool h2 = use_h2_kernel(plan);
@@ -1157,6 +1188,80 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         return rc;
     }
     d.flags = const_cast<unsigned*>(cflags);
+    // kernel A0: few packed pw-linear terms -> metadata into a parameter block; entries listed
+    // direction by direction, finest family first, coarser families of a direction derived from
+    // the fine bracket when their knots are bit-for-bit among the fine ones
+    if (kind == SGM_PW_LINEAR && n_packed == T && T > 0 && T <= sgm::SMALL_MAX_TERMS &&
+        (int)entries.size() <= sgm::SMALL_MAX_ENTRIES && desc->n_seg == 0 && desc->map_off[T] <= 4096) {
+        sgm::SmallPlan& sp = plan->small;
+        std::vector<int> order(entries.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (entries[a].dim != entries[b].dim) return entries[a].dim < entries[b].dim;
+            return entries[a].n > entries[b].n;
+        });
+        std::vector<int> new_id(entries.size());
+        std::vector<unsigned short> tabs;
+        std::vector<double> sk;                             // knots re-packed for this kernel
+        sp.T = (int)T; sp.E = (int)entries.size();
+        int fine = -1;
+        const double inf = std::numeric_limits<double>::infinity();
+        for (size_t q = 0; q < order.size(); ++q) {
+            const Entry& e = entries[order[q]];
+            new_id[order[q]] = (int)q;
+            sgm::SmallEntry& se = sp.ent[q];
+            se.dim_n = e.dim | (e.n << 16);
+            se.knot_off = (int)sk.size();
+            se.tab_off = 0;
+            const double* gc = desc->fam_knots + e.knot_off;
+            bool nested = false;
+            if (q > 0 && entries[order[q - 1]].dim == e.dim) {
+                // tab[cnt] = clip(#{coarse knots among the first cnt fine knots} - 1, 0, n - 2)
+                const Entry& ef = entries[order[fine]];
+                const double* gf = desc->fam_knots + ef.knot_off;
+                std::vector<unsigned short> tab((size_t)ef.n + 1);
+                int jc = 0;
+                tab[0] = 0;
+                for (int i = 0; i < ef.n; ++i) {
+                    if (jc < e.n && std::memcmp(&gf[i], &gc[jc], sizeof(double)) == 0) ++jc;
+                    tab[(size_t)i + 1] = (unsigned short)std::max(0, std::min(jc - 1, e.n - 2));
+                }
+                nested = jc == e.n;                         // every coarse knot is (bitwise) a fine knot
+                if (nested) {
+                    se.from_steps = -1;
+                    se.tab_off = (int)tabs.size();
+                    tabs.insert(tabs.end(), tab.begin(), tab.end());
+                    sk.insert(sk.end(), gc, gc + e.n);
+                }
+            }
+            if (!nested) {                                  // this entry searches: pad with +inf
+                int steps = 1;
+                while ((1 << steps) - 1 < e.n) ++steps;
+                se.from_steps = steps;
+                sk.insert(sk.end(), gc, gc + e.n);
+                sk.insert(sk.end(), (size_t)((1 << steps) - 1 - e.n), inf);
+                fine = (int)q;                              // coarser families derive from the last search
+            }
+        }
+        sp.n_knots = (int)sk.size();
+        sp.n_tab = (int)tabs.size();
+        for (int64_t t = 0; t < T; ++t) {
+            sgm::SmallTerm& st = sp.term[t];
+            const TermRec& r = rec[t];
+            st.coeff = r.coeff; st.val_off = r.val_off; st.k = r.info & 0xff;
+            for (int j = 0; j < 4; ++j) {
+                st.ent[j] = j < st.k ? (unsigned short)new_id[r.ent[j]] : 0;
+                st.stride[j] = r.stride[j];
+            }
+        }
+        const unsigned short* dtabs = nullptr;
+        if ((rc = upload(plan, tabs, &dtabs))) { sgm_plan_destroy(plan); return rc; }
+        const double* dsk = nullptr;
+        if ((rc = upload(plan, sk, &dsk))) { sgm_plan_destroy(plan); return rc; }
+        plan->small_tabs = dtabs;
+        plan->small_knots = dsk;
+        plan->small_ok = true;
+    }
     d.h2_groups = reinterpret_cast<const int4*>(h2g);
     d.h2_parents = h2p;
     d.h2_n_groups = (int)(h2_groups.size() / 12);

@@ -363,6 +363,169 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel A0 ("small"): pw-linear plans with FEW terms evaluated at MANY points (example/1 as
+// shipped: 7 terms, 22 corners per point) -- the regime where the interpolant is HBM-bound:
+// 8 (N + 1) algorithmic bytes per point against a few hundred instructions.  One thread per
+// point.  What makes it cheap:
+//   * all plan metadata (entries, packed term records) travels in the KERNEL PARAMETERS, i.e.
+//     through the constant bank into uniform registers: no warp-wide loads of uniform data
+//     (a 16-byte uniform LDG costs the L1 data pipe as much as a 512-byte gather);
+//   * one binary search per DIRECTION, on its finest knot family; the brackets of the coarser
+//     families of that direction are read from a table indexed by the fine count when their
+//     knots are bit-for-bit a subset of the fine ones (nested families; else they search);
+//   * the bracket coordinate keeps the reference's IEEE division y = (x - g_i) / (g_{i+1} - g_i).
+// Same operations per point and output as kernel A: bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int SMALL_MAX_TERMS = 24, SMALL_MAX_ENTRIES = 16;
+// dim | n << 16; knots of the family at knot_off (searched families: padded with +inf to
+// 2^steps - 1 entries, `steps` = rounds of the branch-free search); from = finest entry of the
+// direction (-1: this entry searches) and its bracket table at tab_off
+struct __align__(16) SmallEntry { int dim_n, knot_off, from_steps, tab_off; };
+struct SmallTerm { double coeff; int val_off, k; unsigned short ent[4], stride[4]; };
+struct SmallPlan {
+    int T, E, n_knots, n_tab;
+    SmallEntry ent[SMALL_MAX_ENTRIES];
+    SmallTerm term[SMALL_MAX_TERMS];
+};
+
+template <int K>
+__device__ __forceinline__ double small_term(const SmallTerm& t, const double* sy, const unsigned short* si,
+                                             int bs, const double* G) {
+    double wl[K], wh[K];
+    unsigned st[K];
+    unsigned base = (unsigned)t.val_off;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double y = sy[(int)t.ent[j] * bs];
+        wh[j] = y;
+        wl[j] = 1.0 - y;
+        st[j] = t.stride[j];
+        base += (unsigned)si[(int)t.ent[j] * bs] * st[j];
+    }
+    double tp = 0.0;
+#pragma unroll
+    for (int c = 0; c < (1 << K); ++c) {              // corners in itertools.product order
+        double w = 1.0;
+        unsigned off = base;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int bit = (c >> (K - 1 - j)) & 1;
+            w = w * (bit ? wh[j] : wl[j]);
+            off += bit ? st[j] : 0u;
+        }
+        tp = tp + G[off] * w;
+    }
+    return tp;
+}
+
+// PPT points per thread (p, p + THREADS, ...): the uniform bookkeeping (parameter loads, loop
+// control, shared-memory addressing) is paid once for PPT points and their dependent chains
+// (search, division, corner sums) interleave.
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS)
+eval_points_small_kernel(const __grid_constant__ SmallPlan sp, const double* __restrict__ knots,
+                         const unsigned short* __restrict__ tabs, const double* __restrict__ x,
+                         int64_t P, int64_t ldx, const int* __restrict__ maps, int n_vals,
+                         const double* __restrict__ f, int64_t ldf,
+                         double* __restrict__ out, int64_t ldo, double scale, int accumulate) {
+    constexpr int BS = THREADS * PPT;                                       // table row length
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* sy_all = sknots + sp.n_knots;                                   // [E][BS]
+    // the node values of all terms (f gathered through the node maps: the reference's per-term
+    // fancy-index copy, sparse_grid_interpolant.py:274) live in shared memory: a corner gather
+    // of 32 lanes into a table of a few KB touches most of its lines when it goes through L1
+    double* G = sy_all + (size_t)sp.E * BS;                                 // [n_vals]
+    unsigned short* si_all = reinterpret_cast<unsigned short*>(G + n_vals);
+    unsigned short* stab = si_all + (size_t)sp.E * BS;                      // derived-bracket tables
+    for (int i = threadIdx.x; i < sp.n_knots; i += THREADS) sknots[i] = knots[i];
+    for (int i = threadIdx.x; i < sp.n_tab; i += THREADS) stab[i] = tabs[i];
+    for (int i = threadIdx.x; i < n_vals; i += THREADS) G[i] = f[(int64_t)maps[i] * ldf];
+    __syncthreads();
+    double* sy = sy_all + threadIdx.x;
+    unsigned short* si = si_all + threadIdx.x;
+    const int64_t n_tiles = (P + BS - 1) / BS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t p[PPT];
+        bool ok[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int64_t pp = tile * BS + q * THREADS + threadIdx.x;
+            ok[q] = pp < P;
+            p[q] = ok[q] ? pp : P - 1;
+        }
+        // entries are listed direction by direction, the finest family of a direction first
+        double xd[PPT];
+        int cnt_fine[PPT], cur_dim = -1;
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) { xd[q] = 0.0; cnt_fine[q] = 0; }
+#pragma unroll 1
+        for (int e = 0; e < sp.E; ++e) {
+            const SmallEntry en = sp.ent[e];
+            const int dim = en.dim_n & 0xffff, n = en.dim_n >> 16;
+            if (dim != cur_dim) {                                            // warp-uniform
+                cur_dim = dim;
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) xd[q] = x[p[q] * ldx + dim];
+            }
+            const double* g = sknots + en.knot_off;
+            int i[PPT];
+            if (en.from_steps >= 0) {
+                // #{g <= x} by a branch-free search over the +inf padded family: one load, one
+                // compare, one select per round (NaN compares false everywhere: 0)
+                int cnt[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) cnt[q] = 0;
+                for (int step = 1 << (en.from_steps - 1); step > 0; step >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) cnt[q] += (g[cnt[q] + step - 1] <= xd[q]) ? step : 0;
+                }
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    cnt_fine[q] = cnt[q];
+                    i[q] = max(0, min(cnt[q] - 1, n - 2));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) i[q] = stab[en.tab_off + cnt_fine[q]];   // nested coarser family
+            }
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                sy[e * BS + q * THREADS] = (xd[q] - g[i[q]]) / (g[i[q] + 1] - g[i[q]]);
+                si[e * BS + q * THREADS] = (unsigned short)i[q];
+            }
+        }
+        double acc[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) acc[q] = 0.0;
+#pragma unroll 1
+        for (int t = 0; t < sp.T; ++t) {
+            const SmallTerm& tm = sp.term[t];
+            double tp[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                switch (tm.k) {
+                    case 0: tp[q] = G[tm.val_off]; break;
+                    case 1: tp[q] = small_term<1>(tm, sy + q * THREADS, si + q * THREADS, BS, G); break;
+                    case 2: tp[q] = small_term<2>(tm, sy + q * THREADS, si + q * THREADS, BS, G); break;
+                    case 3: tp[q] = small_term<3>(tm, sy + q * THREADS, si + q * THREADS, BS, G); break;
+                    default: tp[q] = small_term<4>(tm, sy + q * THREADS, si + q * THREADS, BS, G); break;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) acc[q] = acc[q] + tm.coeff * tp[q];
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            if (!ok[q]) continue;
+            double* o = out + p[q] * ldo;
+            if (accumulate) *o = *o + scale * acc[q];
+            else *o = (scale == 1.0) ? acc[q] : scale * acc[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Kernel A2 ("split"): scalar output, one block = 32 points x W warps.  The 32 lanes of every
 // warp are the 32 points of the tile; the W warps split the TERMS of a chunk among them, so
 // the per-point basis table is stored once per tile (not once per thread) and 16+ warps per

@@ -738,6 +738,42 @@ def test_prefix_kernel_equals_split_kernel_and_oracle(run, monkeypatch):
     assert np.array_equal(it.interpolate(x, f), sg_oracle.interpolate(oracle_plan_of(it), x, f))
 
 
+@pytest.mark.parametrize("shape", ["example1", "not_nested", "three_dirs"])
+def test_small_plan_kernel_few_terms_many_points(shape, monkeypatch):
+    """Kernel A0 (few terms, >= 16384 points: metadata in kernel parameters, coarser brackets of
+    a direction derived from the fine one for bitwise-nested families) against the oracle and,
+    on every point, against kernel A (thread per point, searches per entry)."""
+    rng = np.random.default_rng(77)
+    if shape == "example1":            # example/1 as shipped: unbounded nested knots, 7 terms
+        S = mis.aniso_smolyak_mid_set(5, 10, 2 ** (np.linspace(0, 9, 10)))
+        it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+        x = rng.normal(0, 1.5, (40000, 10))
+    elif shape == "not_nested":        # cc knots with n + 1 points: every family searches
+        it = SGInterpolant(mis.smolyak_mid_set(2, 3), nodes_1d.cc_nodes, lambda n: n + 1, verbose=False)
+        x = rng.uniform(-1.2, 1.2, (33333, 3))
+    else:                              # doubling cc (nested), 3 active directions per term
+        it = SGInterpolant(mis.tensor_product_mid_set(1, 3), nodes_1d.cc_nodes,
+                           lambda n: np.where(n == 0, 1, 2 ** n + 1), verbose=False)
+        x = rng.uniform(-1.1, 1.1, (20001, 3))
+    x[0] = 0.0
+    x[1, 0] = np.nan
+    x[2] = it.SG[-1][:x.shape[1]] if it.SG.shape[1] >= x.shape[1] else 0.0      # exactly on knots
+    assert len(it.combination_coeffs) <= 24
+    f = rng.normal(size=(it.num_nodes, 1))
+    got = it.interpolate(x, f)
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:600], f)
+    assert np.array_equal(got[:600], ref, equal_nan=True)
+    monkeypatch.setenv("SGM_NO_SMALL", "1")
+    reload_knobs()
+    old = it.interpolate(x, f)
+    monkeypatch.delenv("SGM_NO_SMALL")
+    reload_knobs()
+    assert np.array_equal(got, old, equal_nan=True)
+    f3 = rng.normal(size=(it.num_nodes, 3))                # per-column scalar path
+    assert np.array_equal(it.interpolate(x[:20000], f3)[:300],
+                          sg_oracle.interpolate(oracle_plan_of(it), x[:300], f3), equal_nan=True)
+
+
 def test_levy_ciesielski_many_levels_uses_generic_kernel():
     rng = np.random.default_rng(13)
     tt = np.linspace(0, 1, 29)
