@@ -162,6 +162,24 @@ int sgm_plan_reload_knobs(sgm_plan* plan);
 int64_t sgm_plan_table_bytes(const sgm_plan* plan);
 /* sum_t C_t = corner (or node) contributions per point and output: 2^k, 3^k, 4^k or S_t. */
 int64_t sgm_plan_corners_per_point(const sgm_plan* plan);
+/* Plan-specialised kernel for few-term pw-linear plans (csrc/sgm_jit.cpp): when such a plan has
+ * been asked for SGM_JIT_MIN_POINTS (default 4e6) points in total, sgm_eval generates CUDA source
+ * with the plan's tables as literals, compiles it with NVRTC for the device and uses it from
+ * then on (same arithmetic, bit-identical; example/1's shape at 10^7 points: 45 % -> 70 % of the
+ * HBM peak).  Returns 1 = in use, 0 = not built (yet), -1 = unavailable (NVRTC / driver library
+ * missing, compilation failed: the generic kernel stays), 2 = being built; `why` receives a short
+ * description. */
+int sgm_plan_jit_state(sgm_plan* plan, char* why, size_t why_bytes);
+/* The build runs on a background thread (evaluations use the generic kernel meanwhile; 2 = being
+ * built); this waits for a build in progress and returns the state.  SGM_JIT_SYNC=1 builds inside
+ * the triggering sgm_eval instead, SGM_NO_JIT=1 never builds. */
+int sgm_plan_jit_wait(sgm_plan* plan);
+/* Host only (no GPU): the generated source for `desc` with `threads` per block and
+ * `points_per_thread`; SGM_ERR_INVALID when the plan does not qualify.  `*needed` = bytes of the
+ * source incl. the terminator.  compile_cc > 0 (e.g. 100) additionally compiles it with NVRTC
+ * for sm_<cc>a and reports a failure as SGM_ERR_CUDA. */
+int sgm_host_small_kernel_source(const sgm_plan_desc* desc, int32_t threads, int32_t points_per_thread,
+                                 int32_t compile_cc, char* buf, size_t buf_bytes, size_t* needed);
 /* Reads and clears the condition flags set by kernels launched with this plan
  * (synchronises `stream`). */
 int sgm_plan_take_flags(sgm_plan* plan, void* stream, uint32_t* flags);

@@ -41,6 +41,54 @@ def reload_knobs():
             _lib.check(_lib.load().sgm_plan_reload_knobs(plan._h))
 
 
+def make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
+                   fam_newrank=None, seg_off=None):
+    """``sgm_plan_desc`` for the packed tables of an interpolant, plus the arrays it points into
+    (keep them alive as long as the descriptor is used)."""
+    kind, N = int(kind), int(N)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    term_fam = np.ascontiguousarray(term_fam, dtype=np.int32).reshape(-1, N)
+    map_off = np.ascontiguousarray(map_off, dtype=np.int64)
+    maps = np.ascontiguousarray(maps, dtype=np.int32)
+    fam_off = np.ascontiguousarray(fam_off, dtype=np.int64)
+    n_fam = fam_off.size - 1
+    fam_knots = np.ascontiguousarray(fam_knots, dtype=np.float64)
+    lam = None
+    if kind == _lib.KIND_LAGRANGE:
+        lam = np.concatenate([lagrange_lambdas(fam_knots[fam_off[i]:fam_off[i + 1]])
+                              for i in range(n_fam)]) if n_fam else np.zeros(0)
+    newrank = None if fam_newrank is None else np.ascontiguousarray(fam_newrank, dtype=np.int32)
+    seg = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int64)
+    desc = _lib.PlanDesc(
+        kind=kind, N=N, T=coeffs.shape[0], M=int(M),
+        coeffs=_lib.ptr(coeffs, _lib.c_f64), term_fam=_lib.ptr(term_fam, _lib.c_i32),
+        map_off=_lib.ptr(map_off, _lib.c_i64), maps=_lib.ptr(maps, _lib.c_i32),
+        n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
+        fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
+        fam_lambda=_lib.ptr(lam, _lib.c_f64),
+        fam_newrank=_lib.ptr(newrank, _lib.c_i32),
+        n_seg=0 if seg is None else seg.size - 1, seg_off=_lib.ptr(seg, _lib.c_i64))
+    return desc, (coeffs, term_fam, map_off, maps, fam_off, fam_knots, lam, newrank, seg)
+
+
+def small_kernel_source(interp, threads=256, points_per_thread=1, compile_cc=0):
+    """CUDA source of the plan-specialised kernel that ``sgm_eval`` builds for few-term pw-linear
+    interpolants evaluated at many points (csrc/sgm_jit.cpp); host only.  ``compile_cc=100``
+    also compiles it with NVRTC for sm_100a.  ValueError when the plan does not qualify."""
+    desc, keep = make_plan_desc(interp._kind, interp.N, interp.num_nodes, interp._coeffs.astype(np.float64),
+                                interp._term_fam, interp._map_off, interp._maps, interp._fam_off,
+                                interp._fam_knots)
+    lib = _lib.load()
+    need = _lib.c_sz(0)
+    _lib.check(lib.sgm_host_small_kernel_source(ctypes.byref(desc), threads, points_per_thread, 0, None, 0,
+                                                ctypes.byref(need)))
+    buf = ctypes.create_string_buffer(need.value)
+    _lib.check(lib.sgm_host_small_kernel_source(ctypes.byref(desc), threads, points_per_thread, compile_cc,
+                                                buf, need.value, None))
+    del keep
+    return buf.value.decode()
+
+
 class DevicePlan:
     """Packed tables of one interpolant resident on one GPU (sgm_plan)."""
 
@@ -53,31 +101,9 @@ class DevicePlan:
         lib = _lib.load()
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.kind, self.N, self.M = int(kind), int(N), int(M)
-        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
-        term_fam = np.ascontiguousarray(term_fam, dtype=np.int32).reshape(-1, self.N)
-        map_off = np.ascontiguousarray(map_off, dtype=np.int64)
-        maps = np.ascontiguousarray(maps, dtype=np.int32)
-        fam_off = np.ascontiguousarray(fam_off, dtype=np.int64)
-        n_fam = fam_off.size - 1
-        fam_knots = np.ascontiguousarray(fam_knots, dtype=np.float64)
-        lam = None
-        if kind == _lib.KIND_LAGRANGE:
-            lam = np.concatenate([lagrange_lambdas(fam_knots[fam_off[i]:fam_off[i + 1]])
-                                  for i in range(n_fam)]) if n_fam else np.zeros(0)
-        # (named so that it outlives the ctypes call below)
-        newrank = None if fam_newrank is None else np.ascontiguousarray(fam_newrank, dtype=np.int32)
-        self.T = coeffs.shape[0]
-        seg = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int64)
-        self.n_seg = 0 if seg is None else seg.size - 1
-        desc = _lib.PlanDesc(
-            kind=self.kind, N=self.N, T=self.T, M=self.M,
-            coeffs=_lib.ptr(coeffs, _lib.c_f64), term_fam=_lib.ptr(term_fam, _lib.c_i32),
-            map_off=_lib.ptr(map_off, _lib.c_i64), maps=_lib.ptr(maps, _lib.c_i32),
-            n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
-            fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
-            fam_lambda=_lib.ptr(lam, _lib.c_f64),
-            fam_newrank=_lib.ptr(newrank, _lib.c_i32),
-            n_seg=self.n_seg, seg_off=_lib.ptr(seg, _lib.c_i64))
+        desc, self._desc_arrays = make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off,
+                                                 fam_knots, fam_newrank, seg_off)
+        self.T, self.n_seg = int(desc.T), int(desc.n_seg)
         handle = _lib.c_vp()
         _lib.check(lib.sgm_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
         self._h = handle
@@ -173,6 +199,16 @@ class DevicePlan:
 
     def reload_knobs(self):
         _lib.check(_lib.load().sgm_plan_reload_knobs(self._h))
+
+    def jit_wait(self):
+        """Wait for a background build of the plan-specialised kernel; returns its state."""
+        return int(_lib.load().sgm_plan_jit_wait(self._h))
+
+    def jit_state(self):
+        """(state, description) of the plan-specialised kernel: 1 in use, 0 not built, -1 unavailable."""
+        buf = ctypes.create_string_buffer(512)
+        state = int(_lib.load().sgm_plan_jit_state(self._h, buf, 512))
+        return state, buf.value.decode()
 
     def take_flags(self):
         torch = torch_cuda()

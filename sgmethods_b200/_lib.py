@@ -65,6 +65,10 @@ SIGNATURES = {
                                        ctypes.POINTER(c_vp)]),
     "sgm_plan_destroy": (None, [c_vp]),
     "sgm_plan_reload_knobs": (ctypes.c_int, [c_vp]),
+    "sgm_plan_jit_state": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_sz]),
+    "sgm_plan_jit_wait": (ctypes.c_int, [c_vp]),
+    "sgm_host_small_kernel_source": (ctypes.c_int, [ctypes.POINTER(PlanDesc), c_i32, c_i32, c_i32,
+                                                    ctypes.c_char_p, c_sz, ctypes.POINTER(c_sz)]),
     "sgm_eval_segments": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
                                          c_i64, c_i64, c_vp, c_sz, c_vp]),
     "sgm_segment_sumsq": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),

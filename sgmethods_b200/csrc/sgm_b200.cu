@@ -7,11 +7,15 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <limits>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sgm_internal.h"
+#include "sgm_jit.h"
 #include "sgm_kernels.cuh"
 
 namespace {
@@ -60,6 +64,9 @@ struct Knobs {
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
     bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false;
+    bool no_jit = false;         // SGM_NO_JIT: never build the plan-specialised small-plan kernel
+    bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
+    long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
     int wide_pairs = -1;         // SGM_WIDE_PAIRS: -1 = automatic, 0 | 1
     long long col_loop_max = -1; // SGM_COL_LOOP_MAX
     int h2_shape = 0;            // SGM_H2_SHAPE: first launch shape of the grouped hierarchical kernel
@@ -76,6 +83,9 @@ struct Knobs {
         k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
         k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
+        k.no_jit = std::getenv("SGM_NO_JIT") != nullptr;
+        k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
+        if (const char* v = std::getenv("SGM_JIT_MIN_POINTS")) k.jit_min_points = std::atoll(v);
         if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
         if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
         if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 6;
@@ -100,6 +110,17 @@ struct sgm_plan {
     sgm::SmallPlan small{};
     const double* small_knots = nullptr;       // knots re-ordered for kernel A0 (device)
     const unsigned short* small_tabs = nullptr;
+    // plan-specialised variant of kernel A0 (sgm_jit.cpp), built once the plan has seen
+    // knobs.jit_min_points points: state 0 = not tried, 2 = being built (background thread),
+    // 1 = ready, -1 = unavailable (jit_why)
+    SgmJitSmallDesc small_desc;
+    SgmJitKernel small_jit;
+    std::atomic<int> jit_state{0};
+    std::atomic<long long> small_points{0};
+    std::mutex jit_mutex;        // guards jit_why and jit_thread
+    std::thread jit_thread;
+    std::string jit_why;
+    int cc_major = 10, cc_minor = 0;
     int64_t table_bytes = 0;
     int kmax = 0;
     int max_entry_n = 0;         // largest knot family among the table entries
@@ -360,6 +381,70 @@ int launch_points_small(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
     kern<<<(unsigned)nb, TH, smem, stream>>>(sp, plan->small_knots, plan->small_tabs, x, P, ldx, plan->dev.maps,
                                             (int)plan->n_vals, f, ldf, out, ldo, scale, accumulate);
     SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
+// Plan-specialised variant of kernel A0 (sgm_jit.cpp).  Built once per plan, when the plan has
+// been asked for knobs.jit_min_points points in total, by a BACKGROUND thread (NVRTC takes
+// ~0.2 s, 2 s with a cold file cache): evaluations keep using the generic kernel A0 until the
+// specialised one is loaded, so no call ever waits for the compiler.  Returns true when the
+// specialised kernel is ready.
+constexpr int kJitThreads = 256, kJitPointsPerThread = 1;
+void small_jit_build(sgm_plan* plan) {
+    cudaSetDevice(plan->device);
+    cudaFree(nullptr);                                   // the runtime's primary context is current
+    const std::string src = sgm_jit_small_source(plan->small_desc, kJitThreads, kJitPointsPerThread, "sgm_small_jit");
+    std::string why;
+    const bool ok = sgm_jit_build(src, "sgm_small_jit", plan->cc_major, plan->cc_minor, kJitThreads,
+                                  &plan->small_jit, &why);
+    plan->small_jit.ppt = kJitPointsPerThread;
+    {
+        std::lock_guard<std::mutex> lock(plan->jit_mutex);
+        plan->jit_why = ok ? "ready: " + std::to_string(plan->small_jit.regs) + " registers, " +
+                                 std::to_string(plan->small_jit.blocks_per_sm) + " blocks per SM"
+                           : why;
+    }
+    plan->jit_state.store(ok ? 1 : -1, std::memory_order_release);
+}
+bool small_jit_ready(sgm_plan* plan, int64_t P) {
+    if (plan->knobs.no_jit) return false;
+    const int state = plan->jit_state.load(std::memory_order_acquire);
+    if (state != 0) return state == 1;
+    if (plan->small_points.fetch_add(P) + P < plan->knobs.jit_min_points) return false;
+    int expected = 0;
+    if (!plan->jit_state.compare_exchange_strong(expected, 2)) return expected == 1;
+    if (plan->knobs.jit_sync) {
+        DeviceGuard guard(plan->device);
+        small_jit_build(plan);
+        return plan->jit_state.load(std::memory_order_acquire) == 1;
+    }
+    std::lock_guard<std::mutex> lock(plan->jit_mutex);
+    plan->jit_thread = std::thread(small_jit_build, plan);
+    return false;
+}
+void small_jit_join(sgm_plan* plan) {
+    std::thread t;
+    {
+        std::lock_guard<std::mutex> lock(plan->jit_mutex);
+        t.swap(plan->jit_thread);
+    }
+    if (t.joinable()) t.join();
+}
+
+int launch_points_small_jit(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                            int64_t ldf, double* out, int64_t ldo, double scale, int accumulate,
+                            cudaStream_t stream) {
+    const SgmJitKernel& k = plan->small_jit;
+    const int64_t per_tile = (int64_t)k.threads * k.ppt;
+    // three waves of resident blocks: enough tiles per block for the software pipeline, enough
+    // blocks for an even tail
+    const int64_t nb = std::min<int64_t>((P + per_tile - 1) / per_tile, (int64_t)plan->sm_count * k.blocks_per_sm * 3);
+    long long Pll = P, ldxll = ldx, ldfll = ldf, ldoll = ldo;
+    const int* maps = plan->dev.maps;
+    void* args[] = {(void*)&plan->small_knots, (void*)&plan->small_tabs, (void*)&x, &Pll, &ldxll, (void*)&maps,
+                    (void*)&f, &ldfll, (void*)&out, &ldoll, &scale, &accumulate};
+    const int rc = sgm_jit_launch(k, (unsigned)nb, args, stream);
+    if (rc != 0) return sgm_failf(SGM_ERR_CUDA, "launch of the plan-specialised kernel failed (CUresult %d)", rc);
     return SGM_OK;
 }
 
@@ -638,8 +723,11 @@ int eval_one(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const doub
         const size_t g_bytes = g_bytes_of(plan);
         if (workspace_bytes < g_bytes || !workspace)
             return sgm_fail(SGM_ERR_WORKSPACE, "eval: workspace too small");
-        if (kind == SGM_PW_LINEAR && use_small_kernel(plan, P))
+        if (kind == SGM_PW_LINEAR && use_small_kernel(plan, P)) {
+            if (small_jit_ready(plan, P))
+                return launch_points_small_jit(plan, x, P, ldx, f + col, ldf, out + col, ldo, scale, accumulate, stream);
             return launch_points_small(plan, x, P, ldx, f + col, ldf, out + col, ldo, scale, accumulate, stream);
+        }
         double* G = static_cast<double*>(workspace);
         unsigned char* scratch = static_cast<unsigned char*>(workspace) + g_bytes;
         const bool h2 = use_h2_kernel(plan);
@@ -1093,6 +1181,8 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     plan->M = desc->M;
     cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&plan->cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&plan->cc_minor, cudaDevAttrComputeCapabilityMinor, device);
     plan->n_vals = desc->map_off[T];
     plan->corners = corners;
     plan->all_packed = (n_packed == T);
@@ -1190,74 +1280,31 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     d.flags = const_cast<unsigned*>(cflags);
     // kernel A0: few packed pw-linear terms -> metadata into a parameter block; entries listed
     // direction by direction, finest family first, coarser families of a direction derived from
-    // the fine bracket when their knots are bit-for-bit among the fine ones
-    if (kind == SGM_PW_LINEAR && n_packed == T && T > 0 && T <= sgm::SMALL_MAX_TERMS &&
-        (int)entries.size() <= sgm::SMALL_MAX_ENTRIES && desc->n_seg == 0 && desc->map_off[T] <= 4096) {
+    // the fine bracket when their knots are bit-for-bit among the fine ones (sgm_small_plan_build);
+    // the same tables feed the plan-specialised kernel, generated on demand
+    if (kind == SGM_PW_LINEAR && n_packed == T && sgm_small_plan_build(desc, &plan->small_desc)) {
+        const SgmJitSmallDesc& jd = plan->small_desc;
         sgm::SmallPlan& sp = plan->small;
-        std::vector<int> order(entries.size());
-        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            if (entries[a].dim != entries[b].dim) return entries[a].dim < entries[b].dim;
-            return entries[a].n > entries[b].n;
-        });
-        std::vector<int> new_id(entries.size());
-        std::vector<unsigned short> tabs;
-        std::vector<double> sk;                             // knots re-packed for this kernel
-        sp.T = (int)T; sp.E = (int)entries.size();
-        int fine = -1;
-        const double inf = std::numeric_limits<double>::infinity();
-        for (size_t q = 0; q < order.size(); ++q) {
-            const Entry& e = entries[order[q]];
-            new_id[order[q]] = (int)q;
-            sgm::SmallEntry& se = sp.ent[q];
-            se.dim_n = e.dim | (e.n << 16);
-            se.knot_off = (int)sk.size();
-            se.tab_off = 0;
-            const double* gc = desc->fam_knots + e.knot_off;
-            bool nested = false;
-            if (q > 0 && entries[order[q - 1]].dim == e.dim) {
-                // tab[cnt] = clip(#{coarse knots among the first cnt fine knots} - 1, 0, n - 2)
-                const Entry& ef = entries[order[fine]];
-                const double* gf = desc->fam_knots + ef.knot_off;
-                std::vector<unsigned short> tab((size_t)ef.n + 1);
-                int jc = 0;
-                tab[0] = 0;
-                for (int i = 0; i < ef.n; ++i) {
-                    if (jc < e.n && std::memcmp(&gf[i], &gc[jc], sizeof(double)) == 0) ++jc;
-                    tab[(size_t)i + 1] = (unsigned short)std::max(0, std::min(jc - 1, e.n - 2));
-                }
-                nested = jc == e.n;                         // every coarse knot is (bitwise) a fine knot
-                if (nested) {
-                    se.from_steps = -1;
-                    se.tab_off = (int)tabs.size();
-                    tabs.insert(tabs.end(), tab.begin(), tab.end());
-                    sk.insert(sk.end(), gc, gc + e.n);
-                }
-            }
-            if (!nested) {                                  // this entry searches: pad with +inf
-                int steps = 1;
-                while ((1 << steps) - 1 < e.n) ++steps;
-                se.from_steps = steps;
-                sk.insert(sk.end(), gc, gc + e.n);
-                sk.insert(sk.end(), (size_t)((1 << steps) - 1 - e.n), inf);
-                fine = (int)q;                              // coarser families derive from the last search
-            }
+        sp.T = (int)T; sp.E = (int)jd.ents.size();
+        sp.n_knots = (int)jd.knots.size();
+        sp.n_tab = (int)jd.tabs.size();
+        for (int q = 0; q < sp.E; ++q) {
+            const SgmJitSmallDesc::Ent& e = jd.ents[q];
+            sp.ent[q] = sgm::SmallEntry{e.dim | (e.n << 16), e.knot_off, e.steps, e.tab_off};
         }
-        sp.n_knots = (int)sk.size();
-        sp.n_tab = (int)tabs.size();
         for (int64_t t = 0; t < T; ++t) {
+            const SgmJitSmallDesc::Term& jt = jd.terms[t];
             sgm::SmallTerm& st = sp.term[t];
-            const TermRec& r = rec[t];
-            st.coeff = r.coeff; st.val_off = r.val_off; st.k = r.info & 0xff;
+            st.coeff = jt.coeff; st.val_off = jt.val_off; st.k = jt.k;
             for (int j = 0; j < 4; ++j) {
-                st.ent[j] = j < st.k ? (unsigned short)new_id[r.ent[j]] : 0;
-                st.stride[j] = r.stride[j];
+                st.ent[j] = (unsigned short)jt.ent[j];
+                st.stride[j] = (unsigned short)jt.stride[j];
             }
         }
         const unsigned short* dtabs = nullptr;
-        if ((rc = upload(plan, tabs, &dtabs))) { sgm_plan_destroy(plan); return rc; }
+        if ((rc = upload(plan, jd.tabs, &dtabs))) { sgm_plan_destroy(plan); return rc; }
         const double* dsk = nullptr;
-        if ((rc = upload(plan, sk, &dsk))) { sgm_plan_destroy(plan); return rc; }
+        if ((rc = upload(plan, jd.knots, &dsk))) { sgm_plan_destroy(plan); return rc; }
         plan->small_tabs = dtabs;
         plan->small_knots = dsk;
         plan->small_ok = true;
@@ -1308,8 +1355,44 @@ int sgm_plan_reload_knobs(sgm_plan* plan) {
 void sgm_plan_destroy(sgm_plan* plan) {
     if (!plan) return;
     DeviceGuard guard(plan->device);
+    small_jit_join(plan);
     for (void* p : plan->allocations) cudaFree(p);
+    sgm_jit_unload(&plan->small_jit);
     delete plan;
+}
+
+int sgm_plan_jit_wait(sgm_plan* plan) {
+    if (!plan) return 0;
+    small_jit_join(plan);
+    return plan->jit_state.load(std::memory_order_acquire);
+}
+
+int sgm_host_small_kernel_source(const sgm_plan_desc* desc, int32_t threads, int32_t points_per_thread,
+                                 int32_t compile_cc, char* buf, size_t buf_bytes, size_t* needed) {
+    SgmJitSmallDesc jd;
+    if (threads < 32 || threads > 1024 || threads % 32 || points_per_thread < 1 || points_per_thread > 8)
+        return sgm_fail(SGM_ERR_INVALID, "small_kernel_source: bad launch shape");
+    if (!sgm_small_plan_build(desc, &jd))
+        return sgm_fail(SGM_ERR_INVALID, "small_kernel_source: the plan does not qualify for the small-plan kernels");
+    const std::string src = sgm_jit_small_source(jd, threads, points_per_thread, "sgm_small_jit");
+    if (needed) *needed = src.size() + 1;
+    if (buf && buf_bytes) std::snprintf(buf, buf_bytes, "%s", src.c_str());
+    if (compile_cc > 0) {
+        std::vector<char> cubin;
+        std::string why;
+        if (!sgm_jit_compile(src, compile_cc / 10, compile_cc % 10, &cubin, &why))
+            return sgm_failf(SGM_ERR_CUDA, "small_kernel_source: %s", why.c_str());
+    }
+    return SGM_OK;
+}
+
+int sgm_plan_jit_state(sgm_plan* plan, char* why, size_t why_bytes) {
+    if (!plan) return 0;
+    std::lock_guard<std::mutex> lock(plan->jit_mutex);
+    if (why && why_bytes) {
+        std::snprintf(why, why_bytes, "%s", plan->jit_why.c_str());
+    }
+    return plan->jit_state.load();
 }
 
 int64_t sgm_plan_table_bytes(const sgm_plan* plan) { return plan ? plan->table_bytes : 0; }

@@ -774,6 +774,75 @@ def test_small_plan_kernel_few_terms_many_points(shape, monkeypatch):
                           sg_oracle.interpolate(oracle_plan_of(it), x[:300], f3), equal_nan=True)
 
 
+@pytest.mark.parametrize("shape", ["example1", "not_nested", "three_dirs", "nested_not_dyadic"])
+def test_plan_specialised_kernel_equals_generic_small_kernel(shape, monkeypatch):
+    """The NVRTC-generated kernel of a few-term plan (csrc/sgm_jit.cpp; tables as literals,
+    bracket coordinates in registers, next tile's coordinates prefetched) against kernel A0 on
+    every point (bit for bit, NaN and on-knot points included) and against the oracle."""
+    import torch
+    rng = np.random.default_rng(78)
+    if shape == "example1":
+        S = mis.aniso_smolyak_mid_set(5, 10, 2 ** (np.linspace(0, 9, 10)))
+        it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+        x = rng.normal(0, 1.5, (300001, 12))                 # ldx > N, ragged last tile
+    elif shape == "not_nested":
+        it = SGInterpolant(mis.smolyak_mid_set(2, 3), nodes_1d.cc_nodes, lambda n: n + 1, verbose=False)
+        x = rng.uniform(-1.2, 1.2, (33333, 3))
+    elif shape == "three_dirs":
+        it = SGInterpolant(mis.tensor_product_mid_set(1, 3), nodes_1d.cc_nodes,
+                           lambda n: np.where(n == 0, 1, 2 ** n + 1), verbose=False)
+        x = rng.uniform(-1.1, 1.1, (20001, 3))
+    else:      # nested (1, 3, 9, 27 knots: every level keeps the old ones) but not by halving counts
+        knots = lambda n: np.atleast_1d(np.linspace(-1.0, 1.0, int(n))) if n > 1 else np.zeros(1)  # noqa: E731
+        it = SGInterpolant(mis.smolyak_mid_set(3, 2), knots, lambda n: 3 ** n, verbose=False)
+        x = rng.uniform(-1.3, 1.3, (50000, 2))
+    x[0] = 0.0
+    x[1, 0] = np.nan
+    x[2, :it.N] = it.SG[-1]
+    f = rng.normal(size=(it.num_nodes, 1))
+    xd, fd = torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda()
+    monkeypatch.setenv("SGM_NO_JIT", "1")
+    plan0 = it.device_plan()
+    plan0.reload_knobs()
+    generic = plan0.eval(xd, fd).cpu().numpy()
+    assert plan0.jit_state()[0] == 0
+    monkeypatch.delenv("SGM_NO_JIT")
+    monkeypatch.setenv("SGM_JIT_MIN_POINTS", "1")
+    monkeypatch.setenv("SGM_JIT_SYNC", "1")
+    plan0.reload_knobs()
+    got = plan0.eval(xd, fd)
+    state, why = plan0.jit_state()
+    assert state == 1, why
+    assert np.array_equal(got.cpu().numpy(), generic, equal_nan=True)
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:400, :it.N], f)
+    assert np.array_equal(got.cpu().numpy()[:400, 0], ref, equal_nan=True)
+    # accumulate / scale path of the same kernel through the multi-column loop (strided f, out)
+    f3 = rng.normal(size=(it.num_nodes, 3))
+    got3 = plan0.eval(xd[:40000], torch.from_numpy(f3).cuda()).cpu().numpy()
+    assert np.array_equal(got3[:300], sg_oracle.interpolate(oracle_plan_of(it), x[:300, :it.N], f3), equal_nan=True)
+
+
+def test_plan_specialised_kernel_is_built_in_the_background(monkeypatch):
+    """Default mode: the call that crosses the point threshold starts the build on a thread and
+    is itself served by the generic kernel; after sgm_plan_jit_wait the specialised kernel runs.
+    Same bits before and after."""
+    import torch
+    monkeypatch.setenv("SGM_JIT_MIN_POINTS", "50000")
+    monkeypatch.delenv("SGM_JIT_SYNC", raising=False)
+    S = mis.aniso_smolyak_mid_set(5, 10, 2 ** (np.linspace(0, 9, 10)))
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, lambda n: 2 ** (n + 1) - 1, verbose=False)
+    plan = it.device_plan()
+    plan.reload_knobs()
+    x = torch.randn((40000, 10), dtype=torch.float64, device="cuda")
+    f = torch.randn((it.num_nodes, 1), dtype=torch.float64, device="cuda")
+    a = plan.eval(x, f)
+    assert plan.jit_state()[0] == 0                          # 40000 < 50000 points so far
+    b = plan.eval(x, f)                                      # crosses the threshold
+    assert plan.jit_wait() == 1, plan.jit_state()
+    c = plan.eval(x, f)
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_levy_ciesielski_many_levels_uses_generic_kernel():
     rng = np.random.default_rng(13)
     tt = np.linspace(0, 1, 29)
