@@ -35,10 +35,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# DRAM bytes per launch of the evaluation kernel from the committed ncu capture
-# (136.39 MB read + 4.07 MB written for config 2 at 10^6 points; algorithmic: 138.09 MB;
-#  ncu --set full -k regex:eval_points_prefix -s 4 -c 1 python bench.py --steps 2 --warmup 3)
-NCU_TRAFFIC = {("c2", 10 ** 6): 140461568}
+# DRAM bytes per launch of the evaluation kernel from the committed ncu captures of this command
+# (ncu --set full -k regex:eval_hier_groups -s 5 -c 1 python bench.py --steps 2 --warmup 3
+#  --no-extras --no-cpu-baseline -> profiles/r2_h2_groups_c2_ncu_full.txt: 132.63 MB read + 5.47 MB
+#  written; exact kernel, round 1: 136.39 + 4.07 MB; algorithmic: 138.09 MB)
+NCU_TRAFFIC = {("c2", 10 ** 6, "hierarchical"): 138099200, ("c2", 10 ** 6, "combination"): 140461568}
 
 METRIC = "interpolant point-evals x outputs per second (fp64)"
 UNIT = "point-evals*outputs/s"
@@ -118,6 +119,28 @@ def secondary_rooflines(P, corners, terms, kernel_ms, clk):
             "frac_of_l1_floor": t_l1 / t, "frac_of_fp64_floor": t_fp64 / t}
 
 
+def measured_fp64():
+    """FP64 pipe rates measured on the box by tools/mb_fp64 (built by __graft_entry__.build();
+    run live when the binary is there), else the committed record of the same binary
+    (profiles/r2_mb_fp64.json), else None."""
+    exe = os.path.join(ROOT, "tools", "mb_fp64")
+    try:
+        if os.path.exists(exe):
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            rec = json.loads(out.strip().splitlines()[-1])
+            rec["source"] = "tools/mb_fp64 run inside this bench"
+            return rec
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_mb_fp64.json")) as fh:
+            rec = json.load(fh)
+        rec["source"] = "profiles/r2_mb_fp64.json (tools/mb_fp64 on a B200 of this pool)"
+        return rec
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -141,7 +164,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -428,7 +451,7 @@ def run_indicators(torch, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=WORKLOADS)
@@ -618,7 +641,7 @@ def main():
         corners = exact_plan.corners_per_point
         hier = method == "hierarchical"
         gathers = it.hierarchical()._term_fam.shape[0] if hier else corners
-        exact_kernel_ms = main_kernel_ms_list(exact_ms)
+        fp64 = measured_fp64()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": total_ms / args.steps,
@@ -660,12 +683,17 @@ def main():
                                                "needs >= 2 wavefronts"}},
             "exact_mode": {"value": P * NF / (float(np.mean(exact_ms)) * 1e-3), "unit": UNIT,
                            "ms_per_step": float(np.mean(exact_ms)), "steps": exact_steps,
+                           # separately rounded multiply + add per corner (weight prefix reused: one
+                           # more multiply), against the measured DMUL+DADD pair rate
+                           "fp64_floor_ms": None if not fp64 else
+                           1e3 * P * corners * 1.5 / fp64["dmul_dadd_pairs_per_s"],
                            "hbm_frac": bytes_alg / (float(np.mean(exact_ms)) * 1e-3) / 1e9 / peak,
                            "corner_gathers_per_s": P * corners / (float(np.mean(exact_ms)) * 1e-3),
                            "note": "method='combination': the reference's formula bit for bit "
                                    "(sgm_eval on the same batch)"},
             "clocks": clk,
             "wall_s_timed_region": wall,
+            "fp64_pipe_measured": fp64,
         }
         if numpy_ms is not None:
             line["e2e"]["numpy_in_numpy_out"] = {
@@ -705,10 +733,6 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
-
-
-def main_kernel_ms_list(ms):
-    return float(np.mean(ms))
 
 
 def run_scaling_modes(torch, dist, dev, rank, world, flush):

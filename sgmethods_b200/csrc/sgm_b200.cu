@@ -68,6 +68,7 @@ struct Knobs {
     bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
     long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
     int wide_pairs = -1;         // SGM_WIDE_PAIRS: -1 = automatic, 0 | 1
+    int wide_pts = 0;            // SGM_WIDE_PTS: points per warp of the wide column kernel, 0 = automatic, 2 | 4
     long long col_loop_max = -1; // SGM_COL_LOOP_MAX
     int h2_shape = 0;            // SGM_H2_SHAPE: first launch shape of the grouped hierarchical kernel
     static Knobs from_env() {
@@ -87,6 +88,7 @@ struct Knobs {
         k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
         if (const char* v = std::getenv("SGM_JIT_MIN_POINTS")) k.jit_min_points = std::atoll(v);
         if (const char* v = std::getenv("SGM_WIDE_PAIRS")) k.wide_pairs = v[0] == '0' ? 0 : 1;
+        if (const char* v = std::getenv("SGM_WIDE_PTS")) k.wide_pts = std::atoi(v);
         if (const char* v = std::getenv("SGM_COL_LOOP_MAX")) k.col_loop_max = std::atoll(v);
         if (const char* v = std::getenv("SGM_H2_SHAPE")) k.h2_shape = std::max(0, std::atoi(v)) % 6;
         return k;
@@ -244,8 +246,11 @@ SplitKernel split_kernel_for(int warps, int chunk, bool idx8 = false) {
     return sgm::eval_points_split_kernel<KIND, 4, 32>;
 }
 
+// few_tiles: the batch has at most one tile per SM, so resident blocks per SM do not matter and
+// the time is the latency of ONE tile's walk over all terms: most warps per block wins (the
+// per-call validation sample of method="auto": config 2, 256 points: 0.83 -> ~0.25 ms).
 template <int KIND>
-SplitLaunch choose_split_launch(const sgm_plan* plan) {
+SplitLaunch choose_split_launch(const sgm_plan* plan, bool few_tiles = false) {
     const PlanDev& d = plan->dev;
     const size_t fixed_no_idx = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) +
                                 (size_t)d.B * 32 * 8 + 32 * 8 + 64;
@@ -268,8 +273,9 @@ SplitLaunch choose_split_launch(const sgm_plan* plan) {
         int bps = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, c[0] * 32, smem) != cudaSuccess)
             continue;
-        if (bps * c[0] > best_warps || (bps * c[0] == best_warps && bps > best.blocks_per_sm)) {
-            best_warps = bps * c[0];
+        const int score = few_tiles ? (bps > 0 ? c[0] : 0) : bps * c[0];
+        if (score > best_warps || (score == best_warps && bps > best.blocks_per_sm)) {
+            best_warps = score;
             best = SplitLaunch{c[0], c[1], smem, bps, c[2] != 0};
         }
     }
@@ -480,7 +486,7 @@ template <int KIND>
 int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* G,
                         double* out, int64_t ldo, double scale, int accumulate,
                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
-    const SplitLaunch L = choose_split_launch<KIND>(plan);
+    const SplitLaunch L = choose_split_launch<KIND>(plan, (P + 31) / 32 <= plan->sm_count);
     const bool want_v1 = plan->knobs.force_kernel ? plan->knobs.force_kernel == 1
                                                   : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
     if (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8)   // few terms / huge tables
@@ -647,6 +653,31 @@ int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, c
     return SGM_OK;
 }
 
+// Four points per warp on 128-column tiles (kernel C4); same contract as launch_cols_wide2.
+template <int KIND>
+int launch_cols_wide4(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                      int64_t ldf, int64_t ncols, double* out, int64_t ldo, double scale,
+                      int accumulate, const int* perm, cudaStream_t stream, bool* launched) {
+    *launched = false;
+    const PlanDev& d = plan->dev;
+    const size_t fixed = (size_t)d.n_knots * 8 * (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1);
+    const size_t per_warp = 4 * ((size_t)d.B * 8 + (size_t)d.E * 4) + 32 * (32 + 16 + 8);
+    const int warps = 8;
+    const size_t smem = fixed + per_warp * warps + 16;
+    if (smem > (size_t)plan->max_smem_optin / 2) return SGM_OK;    // keep two blocks per SM
+    const int quads_per_block = warps * 4;
+    const int64_t n_tiles = (ncols + 127) / 128;
+    const int64_t gx = ((P + 3) / 4 + quads_per_block - 1) / quads_per_block;
+    if (gx > 0x7fffffff || n_tiles > 65535) return SGM_OK;
+    auto kern = sgm::eval_cols_wide4_kernel<KIND, 2>;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
+        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, quads_per_block, perm, ncols);
+    SGM_CUDA(cudaGetLastError());
+    *launched = true;
+    return SGM_OK;
+}
+
 template <int KIND>
 int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                        int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
@@ -669,7 +700,11 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
             // an odd last column through the guarded narrow kernel
             const int64_t even = NF & ~(int64_t)1;
             const int64_t nt2 = (even + tile - 1) / tile;
-            int rc2 = tile == 256
+            if (plan->knobs.wide_pts == 4 && NF >= 128) {
+                int rc4 = launch_cols_wide4<KIND>(plan, x, P, ldx, f, ldf, even, out, ldo, scale, accumulate, perm, stream, &launched);
+                if (rc4) return rc4;
+            }
+            int rc2 = launched ? SGM_OK : tile == 256
                 ? launch_cols_wide2<KIND, 4>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched)
                 : tile == 128
                 ? launch_cols_wide2<KIND, 2>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched)

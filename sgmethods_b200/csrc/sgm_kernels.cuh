@@ -1735,6 +1735,7 @@ cols_wide2_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int6
                 rowB = pl.maps[h.val_off + offB];
                 last = (cid == h.ncorner - 1);
                 if (last) coef = pl.coeff[t];
+                if (KIND == SGM_HIER_PW_LINEAR) { wA = wA * coef; wB = wB * coef; }   // folded into the weight
             }
             __syncwarp();                                        // previous batch fully read
             sW[lane] = make_double2(wA, wB);
@@ -1753,10 +1754,18 @@ cols_wide2_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int6
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c)
                     v[c] = okc[c] ? __ldg(reinterpret_cast<const double2*>(frA + 64 * c)) : make_double2(0.0, 0.0);
+                // hierarchical-surplus kind: every term is ONE table entry with coefficient 1, and
+                // the form makes no bit-exactness claim: acc = fma(v, w, acc), one FP64 operation
+                // per element instead of three (product, coefficient multiply, add)
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c) {
-                    tpA[c].x = tpA[c].x + v[c].x * wvA;
-                    tpA[c].y = tpA[c].y + v[c].y * wvA;
+                    if (KIND == SGM_HIER_PW_LINEAR) {
+                        accA[c].x = fma(v[c].x, wvA, accA[c].x);
+                        accA[c].y = fma(v[c].y, wvA, accA[c].y);
+                    } else {
+                        tpA[c].x = tpA[c].x + v[c].x * wvA;
+                        tpA[c].y = tpA[c].y + v[c].y * wvA;
+                    }
                 }
                 if (rA != rB) {                                   // warp-uniform
                     const double* frB = fcol + (int64_t)rB * ldf;
@@ -1766,10 +1775,15 @@ cols_wide2_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int6
                 }
 #pragma unroll
                 for (int c = 0; c < CPL2; ++c) {
-                    tpB[c].x = tpB[c].x + v[c].x * wvB;
-                    tpB[c].y = tpB[c].y + v[c].y * wvB;
+                    if (KIND == SGM_HIER_PW_LINEAR) {
+                        accB[c].x = fma(v[c].x, wvB, accB[c].x);
+                        accB[c].y = fma(v[c].y, wvB, accB[c].y);
+                    } else {
+                        tpB[c].x = tpB[c].x + v[c].x * wvB;
+                        tpB[c].y = tpB[c].y + v[c].y * wvB;
+                    }
                 }
-                if (is_last) {
+                if (KIND != SGM_HIER_PW_LINEAR && is_last) {
                     const double cf = sC[cc];
 #pragma unroll
                     for (int c = 0; c < CPL2; ++c) {
@@ -1816,6 +1830,207 @@ eval_cols_wide2_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
     else
         cols_wide2_body<KIND, CPL2, true>(pl, x, P, ldx, f, ldf, out, ldo, scale, accumulate,
                                           pairs_per_block, perm, ncols);
+}
+
+// Kernel C4 ("wide quads"): FOUR points per warp on 128-column tiles (CPL2 = 2: a lane owns two
+// pairs of adjacent columns).  Same list walk as the pair kernel; the four points are consecutive
+// in the locality order, and a row of f is loaded again only when it differs from the row of the
+// previous point of the quad, so a row shared by the whole quad is fetched ONCE for 4 x 4 FP64
+// multiply-adds per lane: the L1 -> register traffic per multiply-add falls to a quarter of the
+// one-point kernel's.  Per point the operations and their order are those of the one-point kernel
+// (bit-identical); the hierarchical-surplus kind, which makes no bit-exactness claim, contracts
+// multiply and add into one FMA.  MEASURED SLOWER than the pair kernel on 256-column tiles
+// (config 3: x0.81, config 4: x0.88, tools/exp_quads.py): the kernel is bound by load latency at 16
+// warps per SM, not by L1 bandwidth, and 128-column tiles repeat the per-point set-up twice as
+// often; kept behind SGM_WIDE_PTS=4 as a record of the experiment.
+template <int KIND, int CPL2, bool GUARD>
+__device__ __forceinline__ void
+cols_wide4_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                int64_t ldo, double scale, int accumulate, int quads_per_block,
+                const int* __restrict__ perm, int64_t ncols) {
+    constexpr int NP = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    double* sknots = reinterpret_cast<double*>(smem_raw);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
+        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+    }
+    double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
+    double* bas0 = sbas_all + (size_t)(NP * warp) * pl.B;
+    // per-warp staging of 32 list entries: 4 weights (32 B) | 4 rows, last flag in the sign bit of
+    // the first (16 B) | coefficient (8 B)
+    unsigned char* stage = reinterpret_cast<unsigned char*>(sbas_all + (size_t)(NP * n_warps) * pl.B);
+    stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;
+    double2* sW = reinterpret_cast<double2*>(stage) + (size_t)warp * 64;
+    int4* sR = reinterpret_cast<int4*>(stage + (size_t)n_warps * 32 * 32) + (size_t)warp * 32;
+    double* sC = reinterpret_cast<double*>(stage + (size_t)n_warps * 32 * 48) + (size_t)warp * 32;
+    int* idx0 = reinterpret_cast<int*>(stage + (size_t)n_warps * 32 * 56) + (size_t)(NP * warp) * pl.E;
+    __syncthreads();
+
+    const int64_t col0 = (int64_t)blockIdx.y * (64 * CPL2) + 2 * lane;
+    const double* fcol = f + col0;
+    bool okc[CPL2];
+#pragma unroll
+    for (int c = 0; c < CPL2; ++c) okc[c] = !GUARD || col0 + 64 * c + 1 < ncols;
+    const int64_t n_quads = (P + NP - 1) / NP;
+    const int64_t q_begin = (int64_t)blockIdx.x * quads_per_block;
+    const int64_t q_end = min(n_quads, q_begin + quads_per_block);
+    for (int64_t q = q_begin + warp; q < q_end; q += n_warps) {
+        int64_t pt[NP];
+        bool has[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            has[j] = NP * q + j < P;
+            const int64_t s = has[j] ? NP * q + j : NP * q;
+            pt[j] = perm ? (int64_t)perm[s] : s;
+        }
+        __syncwarp();
+        for (int e = lane; e < pl.E; e += 32) {
+            const Entry en = pl.ent[e];
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                fill_basis<KIND, int>(en, x[pt[j] * ldx + en.dim], sknots, slambda, bas0 + (size_t)j * pl.B,
+                                      idx0 + (size_t)j * pl.E, e, 1, pl.flags);
+        }
+        __syncwarp();
+        double2 acc[NP][CPL2], tp[NP][CPL2];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+#pragma unroll
+            for (int c = 0; c < CPL2; ++c) {
+                acc[j][c] = make_double2(0.0, 0.0);
+                tp[j][c] = make_double2(0.0, 0.0);
+            }
+        for (int g0 = 0; g0 < pl.n_corners; g0 += 32) {
+            const int g = g0 + lane;
+            double w[NP];
+            int row[NP];
+            double coef = 0.0;
+            int last = 0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { w[j] = 1.0; row[j] = 0; }
+            if (g < pl.n_corners) {
+                const int t = pl.corner_term[g];
+                const TermHdr h = pl.hdr[t];
+                const int cid = g - pl.corner_off[t];
+                const TermDim* td = pl.tdim + h.dim_off;
+                int off[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) off[j] = 0;
+                int cs = h.ncorner;
+                int rem = cid;
+                for (int jd = 0; jd < h.k; ++jd) {
+                    const TermDim d = td[jd];
+                    int a;
+                    if (KIND == SGM_LAGRANGE) {
+                        cs /= d.radix;
+                        a = (cid / cs) % d.radix;
+                    } else {
+                        constexpr int R = fixed_radix(KIND);
+                        cs /= R;
+                        a = rem / cs;
+                        rem -= a * cs;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        w[j] = w[j] * digit_weight<KIND>(bas0 + (size_t)j * pl.B, 1, d, a);
+                        off[j] += (idx0[(size_t)j * pl.E + d.ent] + a) * d.stride;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NP; ++j) row[j] = pl.maps[h.val_off + off[j]];
+                last = (cid == h.ncorner - 1);
+                if (last) coef = pl.coeff[t];
+                if (KIND == SGM_HIER_PW_LINEAR) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) w[j] = w[j] * coef;                   // folded into the weight
+                }
+            }
+            __syncwarp();                                        // previous batch fully read
+            sW[2 * lane] = make_double2(w[0], w[1]);
+            sW[2 * lane + 1] = make_double2(w[2], w[3]);
+            sR[lane] = make_int4(row[0] | (last << 31), row[1], row[2], row[3]);
+            sC[lane] = coef;
+            __syncwarp();
+            const int n_in = min(32, pl.n_corners - g0);
+            for (int cc = 0; cc < n_in; ++cc) {
+                const double2 w01 = sW[2 * cc], w23 = sW[2 * cc + 1];
+                const int4 rr = sR[cc];
+                const int r0 = rr.x & 0x7fffffff;
+                const int is_last = rr.x < 0;
+                const int rj[NP] = {r0, rr.y, rr.z, rr.w};
+                const double wj[NP] = {w01.x, w01.y, w23.x, w23.y};
+                double2 v[CPL2];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    if (j == 0 || rj[j] != rj[j - 1]) {           // warp-uniform
+                        const double* fr = fcol + (int64_t)rj[j] * ldf;
+#pragma unroll
+                        for (int c = 0; c < CPL2; ++c)
+                            v[c] = okc[c] ? __ldg(reinterpret_cast<const double2*>(fr + 64 * c)) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CPL2; ++c) {
+                        if (KIND == SGM_HIER_PW_LINEAR) {         // one entry per term, coefficient 1
+                            acc[j][c].x = fma(v[c].x, wj[j], acc[j][c].x);
+                            acc[j][c].y = fma(v[c].y, wj[j], acc[j][c].y);
+                        } else {
+                            tp[j][c].x = tp[j][c].x + v[c].x * wj[j];
+                            tp[j][c].y = tp[j][c].y + v[c].y * wj[j];
+                        }
+                    }
+                }
+                if (KIND != SGM_HIER_PW_LINEAR && is_last) {
+                    const double cf = sC[cc];
+#pragma unroll
+                    for (int j = 0; j < NP; ++j)
+#pragma unroll
+                        for (int c = 0; c < CPL2; ++c) {
+                            acc[j][c].x = acc[j][c].x + cf * tp[j][c].x;
+                            acc[j][c].y = acc[j][c].y + cf * tp[j][c].y;
+                            tp[j][c] = make_double2(0.0, 0.0);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            if (!has[j]) continue;
+            double* o = out + pt[j] * ldo + col0;
+#pragma unroll
+            for (int c = 0; c < CPL2; ++c) {
+                if (!okc[c]) continue;
+                double2* dst = reinterpret_cast<double2*>(o + 64 * c);
+                double2 r = make_double2(scale * acc[j][c].x, scale * acc[j][c].y);
+                if (accumulate) {
+                    const double2 old = *dst;
+                    r.x = old.x + r.x;
+                    r.y = old.y + r.y;
+                }
+                *dst = r;
+            }
+        }
+    }
+}
+
+template <int KIND, int CPL2>
+__global__ void __launch_bounds__(256, 2)
+eval_cols_wide4_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                       const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                       int64_t ldo, double scale, int accumulate, int quads_per_block,
+                       const int* __restrict__ perm, int64_t ncols) {
+    if (((int64_t)blockIdx.y + 1) * (64 * CPL2) <= ncols)        // block-uniform
+        cols_wide4_body<KIND, CPL2, false>(pl, x, P, ldx, f, ldf, out, ldo, scale, accumulate,
+                                           quads_per_block, perm, ncols);
+    else
+        cols_wide4_body<KIND, CPL2, true>(pl, x, P, ldx, f, ldf, out, ldo, scale, accumulate,
+                                          quads_per_block, perm, ncols);
 }
 
 // One batch of the dimension-wise hierarchisation (surplus = value - coarser interpolant).
