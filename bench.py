@@ -345,6 +345,14 @@ def run_extra(torch, name, dev, flush, peak, steps=2):
             fx = lambda: it.interpolate(x, f, method="combination")   # noqa: E731
             fx()
             extra["exact_ms"] = float(np.min(timed_steps(torch, fx, steps, flush)))
+    else:
+        extra["auto_validation"] = mli.auto_validation
+        extra["method"] = "hierarchical" if (mli.auto_validation or {}).get("enabled") else "combination"
+        if extra["method"] == "hierarchical":
+            extra["basis_tuples"] = int(mli._hierarchical()[0][-1].n_terms)
+            fx = lambda: mli.interpolate(yy, ml, method="combination")   # noqa: E731
+            fx()
+            extra["exact_ms"] = float(np.min(timed_steps(torch, fx, min(steps, 2), flush)))
     out = {"workload": desc, "points": P, "NF": NF, "ms_per_step": ms, "value": P * NF / ms * 1e3,
            "unit": UNIT, "algorithmic_bytes": bytes_alg, "hbm_gbs": bytes_alg / ms / 1e6,
            "hbm_frac": bytes_alg / ms / 1e6 / peak, "host_setup_s": build_s, "timing": f"best of {steps}"}

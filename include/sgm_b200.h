@@ -47,12 +47,32 @@ typedef enum sgm_kind {
     SGM_PW_CUBIC = 2,         /* TPPwCubicInterpolator     tp_inteprolants.py:162-277 */
     SGM_LAGRANGE = 3,         /* TPLagrangeInterpolator    tp_inteprolants.py:279-360 */
     /* 4 is reserved (internal flavour).  Kind 5 has no reference class: it is the
-     * work-reduced HIERARCHICAL-SURPLUS form of the pw-linear interpolant on nested knots,
-     * sum over ALL multi-indices nu of surplus(nu, j(x)) * prod_d phi_{nu_d}(x_d) with one
-     * basis function per level and direction.  Mathematically equal to the combination
-     * formula, NOT bit-identical to it (it is the more accurate of the two); opt-in only. */
-    SGM_HIER_PW_LINEAR = 5
+     * work-reduced HIERARCHICAL-SURPLUS form of an interpolant on nested knots (csrc and
+     * sgmethods_b200/hierarchical.py): every (direction, level) entry has exactly ONE basis
+     * function that is non-zero at a point, so a multi-index costs one table read and at most
+     * k multiplies.  Which function that is, is a property of the knot family (sgm_hier_basis,
+     * desc.fam_basis): the hat of the bracket's new knot (pw-linear), the middle cardinal
+     * function of the 3-knot patch (pw-quadratic), or the Lagrange cardinal polynomial of the
+     * family's one new knot (Lagrange; also the two end knots of the first 3-knot
+     * pw-quadratic level).  Mathematically equal to the combination formula, NOT
+     * bit-identical to it (it avoids the alternating sum and is the more accurate of the two). */
+    SGM_HIER_PW_LINEAR = 5,
+    SGM_HIER = 5
 } sgm_kind;
+
+/* One-basis-per-entry functions of kind SGM_HIER, per knot family (desc.fam_basis). */
+typedef enum sgm_hier_basis {
+    SGM_HB_HAT = 0,           /* pw-linear: every bracket has one new knot; its hat at x (linear
+                                 extrapolation outside the knots like scipy's RegularGridInterpolator) */
+    SGM_HB_QUAD_MID = 1,      /* pw-quadratic: new knots = odd positions = middle knots of the
+                                 patches [g_2j, g_2j+2]; value of the middle cardinal parabola of
+                                 the patch of x (patch search of tp_inteprolants.py:111-127) */
+    SGM_HB_LAG_ONE = 2,       /* Lagrange: the family has ONE new knot p; value of
+                                 prod_{i != p} (x - g_i) / (g_p - g_i); NaN when x is a knot of the
+                                 family (the reference's barycentric formula gives NaN there) */
+    SGM_HB_QUAD_END = 3       /* like LAG_ONE on a 3-knot family, without the NaN rule and with the
+                                 pw-quadratic "right of the last knot" flag */
+} sgm_hier_basis;
 
 /* Bits reported by sgm_plan_take_flags(): conditions on which the reference raises. */
 #define SGM_FLAG_QUADRATIC_RIGHT 1u  /* pw-quadratic point right of the last knot or NaN:
@@ -142,9 +162,10 @@ typedef struct sgm_plan_desc {
     const int64_t* fam_off;    /* n_fam+1 offsets into fam_knots / fam_lambda               */
     const double* fam_knots;   /* knots of each family, ascending, >= 2 per family          */
     const double* fam_lambda;  /* barycentric lambda per knot (SGM_LAGRANGE only, else NULL) */
-    const int32_t* fam_newrank;/* SGM_HIER_PW_LINEAR only: per knot its rank among the knots
-                                  that are NEW on this level, -1 for knots of the coarser
-                                  level; term tables then have one entry per new-knot tuple */
+    const int32_t* fam_newrank;/* SGM_HIER only: per knot its rank among the knots of the family
+                                  that are NEW on its level (and belong to this family), -1 for
+                                  the others; term tables then have one entry per new-knot tuple */
+    const int32_t* fam_basis;  /* SGM_HIER only: n_fam sgm_hier_basis values, NULL = all SGM_HB_HAT */
     int32_t n_seg;             /* 0: ordinary plan.  > 0: SEGMENTED plan -- the terms form n_seg
                                   consecutive groups, each an independent small interpolant
                                   (e.g. the hierarchical surplus of one refinement candidate);

@@ -42,7 +42,7 @@ def reload_knobs():
 
 
 def make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
-                   fam_newrank=None, seg_off=None):
+                   fam_newrank=None, seg_off=None, fam_basis=None):
     """``sgm_plan_desc`` for the packed tables of an interpolant, plus the arrays it points into
     (keep them alive as long as the descriptor is used)."""
     kind, N = int(kind), int(N)
@@ -58,6 +58,7 @@ def make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_kno
         lam = np.concatenate([lagrange_lambdas(fam_knots[fam_off[i]:fam_off[i + 1]])
                               for i in range(n_fam)]) if n_fam else np.zeros(0)
     newrank = None if fam_newrank is None else np.ascontiguousarray(fam_newrank, dtype=np.int32)
+    basis = None if fam_basis is None else np.ascontiguousarray(fam_basis, dtype=np.int32)
     seg = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int64)
     desc = _lib.PlanDesc(
         kind=kind, N=N, T=coeffs.shape[0], M=int(M),
@@ -66,9 +67,9 @@ def make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_kno
         n_fam=n_fam, fam_off=_lib.ptr(fam_off, _lib.c_i64),
         fam_knots=_lib.ptr(fam_knots, _lib.c_f64),
         fam_lambda=_lib.ptr(lam, _lib.c_f64),
-        fam_newrank=_lib.ptr(newrank, _lib.c_i32),
+        fam_newrank=_lib.ptr(newrank, _lib.c_i32), fam_basis=_lib.ptr(basis, _lib.c_i32),
         n_seg=0 if seg is None else seg.size - 1, seg_off=_lib.ptr(seg, _lib.c_i64))
-    return desc, (coeffs, term_fam, map_off, maps, fam_off, fam_knots, lam, newrank, seg)
+    return desc, (coeffs, term_fam, map_off, maps, fam_off, fam_knots, lam, newrank, seg, basis)
 
 
 def small_kernel_source(interp, threads=256, points_per_thread=1, compile_cc=0):
@@ -93,7 +94,7 @@ class DevicePlan:
     """Packed tables of one interpolant resident on one GPU (sgm_plan)."""
 
     def __init__(self, kind, N, M, coeffs, term_fam, map_off, maps, fam_off, fam_knots,
-                 device=None, fam_newrank=None, seg_off=None):
+                 device=None, fam_newrank=None, seg_off=None, fam_basis=None):
         """term_fam: (T, N) knot-family index per direction, -1 where the term has one node;
         fam_off / fam_knots: CSR list of the families' ascending knot vectors; seg_off: term
         offsets of the segments of a segmented plan (``eval_segments`` / ``surplus_norms``)."""
@@ -102,7 +103,7 @@ class DevicePlan:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.kind, self.N, self.M = int(kind), int(N), int(M)
         desc, self._desc_arrays = make_plan_desc(kind, N, M, coeffs, term_fam, map_off, maps, fam_off,
-                                                 fam_knots, fam_newrank, seg_off)
+                                                 fam_knots, fam_newrank, seg_off, fam_basis)
         self.T, self.n_seg = int(desc.T), int(desc.n_seg)
         handle = _lib.c_vp()
         _lib.check(lib.sgm_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))

@@ -21,7 +21,9 @@ SGM_OK = 0
 SGM_ERR_INVALID, SGM_ERR_CUDA, SGM_ERR_OVERFLOW, SGM_ERR_NODE_TOL, SGM_ERR_WORKSPACE = \
     -1, -2, -3, -4, -5
 KIND_LINEAR, KIND_QUADRATIC, KIND_CUBIC, KIND_LAGRANGE = 0, 1, 2, 3
-KIND_HIER_LINEAR = 5
+KIND_HIER_LINEAR = 5          # SGM_HIER: one-basis-per-entry hierarchical form
+KIND_HIER = 5
+HB_HAT, HB_QUAD_MID, HB_LAG_ONE, HB_QUAD_END = 0, 1, 2, 3     # sgm_hier_basis
 FLAG_QUADRATIC_RIGHT = 1
 
 c_i32, c_i64, c_f64, c_vp, c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
@@ -34,7 +36,7 @@ class PlanDesc(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("N", c_i32), ("T", c_i64), ("M", c_i64),
                 ("coeffs", p_f64), ("term_fam", p_i32), ("map_off", p_i64), ("maps", p_i32),
                 ("n_fam", c_i32), ("fam_off", p_i64), ("fam_knots", p_f64),
-                ("fam_lambda", p_f64), ("fam_newrank", p_i32),
+                ("fam_lambda", p_f64), ("fam_newrank", p_i32), ("fam_basis", p_i32),
                 ("n_seg", c_i32), ("seg_off", p_i64)]
 
 

@@ -68,8 +68,7 @@ struct PlanDev {
     const int* corner_off;             // T+1 prefix sums of the terms' corner counts
     int n_corners;                     // sum_t C_t (0 if the list is not built)
     const double* knots;
-    const double* lambda;
-    const short* newrank;              // SGM_HIER_PW_LINEAR: rank of a knot among the new knots, -1 old
+    const double* lambda;              // Lagrange: barycentric weights; SGM_HIER: per-family new-knot ranks / basis id / denominator
     const TermRec* hrec;               // SGM_HIER_PW_LINEAR: records grouped by number of directions
     int hgroup[6];                     // hrec[hgroup[k] .. hgroup[k+1]) = terms with k directions
     // grouped hierarchical kernel (H2, sgm_hier_host.cpp): group headers, parent paths, 8-byte
@@ -121,16 +120,54 @@ __device__ __forceinline__ void fill_basis(const Entry e, double x, const double
     const int n = e.n;
     double* b = bas + (size_t)e.boff * bs;
     if (KIND == SGM_HIER_PW_LINEAR) {
-        // bracket as for pw-linear; exactly one end of the bracket is a knot that is new on
-        // this level: its hat value at x is the only non-zero hierarchical basis function
-        // (`lambda` carries the new-knot ranks of this plan kind, stored as doubles' bits)
-        const short* nr = reinterpret_cast<const short*>(lambda) + e.knot_off;
-        int i = count_le(g, n, x) - 1;
-        i = max(0, min(i, n - 2));
-        const double y = (x - g[i]) / (g[i + 1] - g[i]);
-        const int r_lo = nr[i];
-        b[0] = r_lo >= 0 ? 1.0 - y : y;
-        idx[(size_t)ent_id * bs] = (IdxT)(r_lo >= 0 ? r_lo : nr[i + 1]);
+        // ONE non-zero hierarchical basis function per entry; which one is a property of the
+        // knot family (sgm_hier_basis).  `lambda` carries, per family, the new-knot ranks as
+        // shorts, the basis id in short n and the one-knot denominator in the last double.
+        const short* nr = reinterpret_cast<const short*>(lambda + e.knot_off);
+        const int hb = nr[n];
+        if (hb == SGM_HB_HAT) {
+            // bracket as for pw-linear; exactly one end of the bracket is a knot that is new on
+            // this level: its hat value at x
+            int i = count_le(g, n, x) - 1;
+            i = max(0, min(i, n - 2));
+            const double y = (x - g[i]) / (g[i + 1] - g[i]);
+            const int r_lo = nr[i];
+            b[0] = r_lo >= 0 ? 1.0 - y : y;
+            idx[(size_t)ent_id * bs] = (IdxT)(r_lo >= 0 ? r_lo : nr[i + 1]);
+        } else if (hb == SGM_HB_QUAD_MID) {
+            // patch search of the pw-quadratic operator; the new knot is the patch's middle knot
+            const int H = (n + 1) >> 1;
+            const int j = max(count_lt_strided(g, H, 2, x) - 1, 0);
+            if (j > H - 2 || x != x) {
+                atomicOr(flags, SGM_FLAG_QUADRATIC_RIGHT);
+                b[0] = __longlong_as_double(0x7ff8000000000000ll);
+                idx[(size_t)ent_id * bs] = (IdxT)0;
+                return;
+            }
+            const double x0 = g[2 * j], x1 = g[2 * j + 1], x2 = g[2 * j + 2];
+            b[0] = ((x - x0) * (x - x2)) / ((x1 - x0) * (x1 - x2));
+            idx[(size_t)ent_id * bs] = (IdxT)nr[2 * j + 1];
+        } else {
+            // cardinal polynomial of the family's one new knot over all knots of the family
+            double num = 1.0;
+            bool hit = false;
+            for (int i = 0; i < n; ++i) {
+                const double dx = x - g[i];
+                hit = hit || dx == 0.0;
+                if (nr[i] < 0) num = num * dx;
+            }
+            double v = num / reinterpret_cast<const double*>(lambda + e.knot_off)[n - 1];
+            if (hb == SGM_HB_QUAD_END) {
+                if (x > g[n - 1] || x != x) {
+                    atomicOr(flags, SGM_FLAG_QUADRATIC_RIGHT);
+                    v = __longlong_as_double(0x7ff8000000000000ll);
+                }
+            } else if (hit) {
+                v = __longlong_as_double(0x7ff8000000000000ll);   // the reference's 0/0 on a knot
+            }
+            b[0] = v;
+            idx[(size_t)ent_id * bs] = (IdxT)0;
+        }
     } else if (base_kind(KIND) == SGM_PW_LINEAR) {
         int i = count_le(g, n, x) - 1;
         i = max(0, min(i, n - 2));
@@ -307,8 +344,7 @@ __global__ void eval_points_kernel(const PlanDev pl, const double* __restrict__ 
     double* slambda = sknots + pl.n_knots;
     for (int i = tid; i < pl.n_knots; i += bs) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     unsigned char* after = reinterpret_cast<unsigned char*>(
         sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots);
@@ -617,8 +653,7 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     double* bas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* sP = bas_all + (size_t)pl.B * 32;                 // [2][chunk][32]
@@ -1019,7 +1054,7 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        slambda[i] = pl.lambda[i];
     }
     double* bas_all = sknots + 2 * (size_t)pl.n_knots;
     double* sPart = bas_all + (size_t)pl.B * 32;              // [W][32]
@@ -1150,7 +1185,7 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        slambda[i] = pl.lambda[i];
     }
     // bracket tables [E + 1][32]: row E is the DUMMY entry (hat value 1, rank 0) that unused
     // member slots and the root group point to, so the member set-up needs no predicates
@@ -1368,8 +1403,7 @@ __global__ void eval_cols_kernel(const PlanDev pl, const double* __restrict__ x,
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* bas = sbas_all + (size_t)warp * pl.B;
@@ -1525,8 +1559,7 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* bas = sbas_all + (size_t)warp * pl.B;
@@ -1654,8 +1687,7 @@ cols_wide2_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int6
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* basA = sbas_all + (size_t)(2 * warp) * pl.B;
@@ -1858,8 +1890,7 @@ cols_wide4_body(const PlanDev& pl, const double* __restrict__ x, int64_t P, int6
     double* slambda = sknots + pl.n_knots;
     for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
         sknots[i] = pl.knots[i];
-        if (KIND == SGM_LAGRANGE) slambda[i] = pl.lambda[i];
-        if (KIND == SGM_HIER_PW_LINEAR) reinterpret_cast<short*>(slambda)[i] = pl.newrank[i];
+        if (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR) slambda[i] = pl.lambda[i];
     }
     double* sbas_all = sknots + (KIND == SGM_LAGRANGE || KIND == SGM_HIER_PW_LINEAR ? 2 : 1) * (size_t)pl.n_knots;
     double* bas0 = sbas_all + (size_t)(NP * warp) * pl.B;

@@ -21,6 +21,19 @@ composed into the node maps of the coarser part -- no copy, and the bracket tabl
 are built once for all parts instead of once per part.  The fused sum runs over all terms
 in one chain, which re-associates the reference's ``out += I_k - I_{k-1}`` (a few ulp of the
 partial sums; the fixtures are met to 1e-12).
+
+Work-reduced form (``interpolate(..., method="auto")``, the default): when the levels share
+operator and knots, their multi-index sets are nested and the hierarchical-surplus form exists
+(hierarchical.py), the surpluses of a function do not depend on the set they are computed in,
+so (I_k - I_{k-1})[s] = sum over the multi-indices of Lambda_k that are not in Lambda_{k-1} of
+their surplus terms, and the whole multilevel sum is ONE hierarchical evaluation on the finest
+set whose surplus table is assembled level by level:
+
+    u_ML = sum_k  sum_{nu in Lambda_k minus Lambda_{k-1}}  Delta_nu [ s_{K-k} ]
+
+(config 4: 705 table reads per point and output instead of the node contributions of
+1 + 2K combination-technique interpolants).  It is validated on every call against the exact
+fused launch on a sample of the batch, like ``SGInterpolant.interpolate``.
 """
 import numpy as np
 
@@ -37,6 +50,8 @@ class MLInterpolant:
         self.interp_seq = interpolants_sequence
         self._restricted = {}
         self._plans = {}
+        self._hier = None
+        self.auto_validation = None
 
     # ----------------------------------------------------------------------------- sampling
     def sample(self, f_approx):
@@ -130,10 +145,89 @@ class MLInterpolant:
         self._plans[key] = (plan, [block_off[b] for b in sorted(block_off)], total + 1, n_max)
         return self._plans[key]
 
-    def _evaluate(self, parts, blocks, yy, missing):
+    # ------------------------------------------------------------- work-reduced form
+    def _hierarchical(self):
+        """Tables of the multilevel sum in hierarchical-surplus form, or NotImplementedError.
+        Returns (plans, moves): ``plans[k]`` the HierarchicalPlan of ``interp_seq[k]``,
+        ``moves[k]`` = (rows of the finest plan's surplus table, rows of level k's surplus
+        table) for the basis tuples that appear on level k for the first time."""
+        if self._hier is not None:
+            if isinstance(self._hier, Exception):
+                raise self._hier
+            return self._hier
+        try:
+            seq = self.interp_seq
+            if len({it._kind for it in seq}) != 1:
+                raise NotImplementedError("levels with different operators")
+            hps = [it.hierarchical() for it in seq]
+            top = hps[-1]
+            n_top = seq[-1].N
+            codes = {}
+
+            def rows_of(hp):
+                """one bytes key per basis tuple: family identities per direction, zero-padded"""
+                lut = np.array([codes.setdefault(k, len(codes) + 1) for k in hp.fam_key] + [0], dtype=np.int64)
+                tf = hp._term_fam
+                if tf.shape[1] > n_top:
+                    raise NotImplementedError("a coarser level has more directions than the finest")
+                mat = np.zeros((tf.shape[0], n_top), dtype=np.int64)
+                mat[:, :tf.shape[1]] = lut[tf]                      # -1 (inactive) -> 0
+                return [r.tobytes() for r in mat]
+
+            for hp in hps:                                          # same knots on every level
+                for m, g in zip([k.size for k in hp.rank_knots], hp.rank_knots):
+                    mine = [t for t in top.rank_knots if t.size == m]
+                    if not mine or not np.array_equal(mine[0], g):
+                        raise NotImplementedError("the levels do not share their knot families")
+            top_rows = rows_of(top)
+            first_level = np.full(len(top_rows), -1, dtype=np.int64)
+            where = np.zeros(len(top_rows), dtype=np.int64)
+            for k in range(len(seq) - 1, -1, -1):
+                index = {r: i for i, r in enumerate(rows_of(hps[k]))}
+                if k < len(seq) - 1 and any(r not in prev for r in index):
+                    raise NotImplementedError("the multi-index sets of the levels are not nested")
+                prev = index
+                for i, r in enumerate(top_rows):
+                    j = index.get(r)
+                    if j is not None:
+                        first_level[i], where[i] = k, j
+            moves = []
+            for k, hp in enumerate(hps):
+                t_top = np.flatnonzero(first_level == k)
+                t_k = where[t_top]
+                sizes = np.diff(top._map_off)[t_top]
+                if not np.array_equal(sizes, np.diff(hp._map_off)[t_k]):
+                    raise NotImplementedError("surplus blocks of different shape")
+                inner = np.arange(int(sizes.sum()), dtype=np.int64) - np.repeat(
+                    np.concatenate(([0], np.cumsum(sizes)))[:-1], sizes)
+                moves.append((np.repeat(top._map_off[t_top], sizes) + inner,
+                              np.repeat(hp._map_off[t_k], sizes) + inner))
+            self._hier = (hps, moves)
+        except NotImplementedError as exc:
+            self._hier = exc
+            raise
+        return self._hier
+
+    def _hier_surpluses(self, torch, fs, device):
+        """Surplus table of the finest plan assembled level by level (block k = samples on the
+        grid of ``interp_seq[k]``)."""
+        hps, moves = self._hierarchical()
+        top = hps[-1]
+        alpha = torch.empty((top.M, fs[0].shape[1]), dtype=torch.float64, device=device)
+        cache = self.__dict__.setdefault("_hier_moves_dev", {})
+        for k, (hp, f) in enumerate(zip(hps, fs)):
+            key = (device.index, k)
+            if key not in cache:
+                cache[key] = tuple(torch.from_numpy(a).to(device) for a in moves[k])
+            dst, src = cache[key]
+            if dst.numel():
+                alpha.index_copy_(0, dst, hp.surpluses(f[:hp.M]).index_select(0, src))
+        return top._dev(device.index)[0], alpha
+
+    def _evaluate(self, parts, blocks, yy, missing, method="combination"):
         """parts as in ``_fused_plan``; blocks: list of sample arrays (block id = position)."""
         from ._device import torch_cuda
-        from .sparse_grid_interpolant import _to_device
+        from .sparse_grid_interpolant import AUTO_MIN_POINTS, AUTO_SAMPLE, AUTO_TOL, _to_device
         torch = torch_cuda()
         as_torch = isinstance(yy, torch.Tensor)
         device = yy.device if as_torch and yy.is_cuda else \
@@ -153,8 +247,33 @@ class MLInterpolant:
                 raise IndexError(f"samples of shape {tuple(f.shape)} given for a sparse grid with "
                                  f"{self.interp_seq[grid].num_nodes} nodes and {NF} outputs")
             F[off:off + f.shape[0]] = f
-        out = plan.eval(x, F)
-        if plan.kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
+        hier = None
+        if method == "hierarchical" or (method == "auto" and x.shape[0] >= AUTO_MIN_POINTS and
+                                        not isinstance(self._hier, Exception)):
+            try:
+                hier = self._hier_surpluses(torch, fs, device)
+            except NotImplementedError as exc:
+                if method == "hierarchical":
+                    raise
+                self.auto_validation = {"enabled": False, "reason": str(exc)}
+        if hier is not None and method == "auto":
+            # validate THIS call: a sample of the batch through both forms, like SGInterpolant
+            xs = x[::max(1, x.shape[0] // AUTO_SAMPLE)][:AUTO_SAMPLE].contiguous()
+            exact, fast = plan.eval(xs, F), hier[0].eval(xs, hier[1])
+            both_nan = exact.isnan() & fast.isnan()
+            scale = torch.where(both_nan, torch.zeros_like(exact), exact.abs()).max()
+            dev = float(torch.where(both_nan, torch.zeros_like(exact), (fast - exact).abs()).max() /
+                        torch.where(scale > 0, scale, torch.ones_like(scale)))
+            ok = bool(np.isfinite(dev)) and dev <= AUTO_TOL
+            self.auto_validation = {"enabled": ok, "max_rel_deviation": dev, "tolerance": AUTO_TOL,
+                                    "sample_points": int(xs.shape[0])}
+            if not ok:
+                hier = None
+        out = plan.eval(x, F) if hier is None else hier[0].eval(x, hier[1])
+        flags = plan.take_flags() if plan.kind == _lib.KIND_QUADRATIC else 0
+        if hier is not None and plan.kind == _lib.KIND_QUADRATIC:
+            flags |= hier[0].take_flags()
+        if flags & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
                              "(or is NaN)")
         # the reference returns np.squeeze'd arrays (every SGInterpolant.interpolate does, :279)
@@ -164,17 +283,25 @@ class MLInterpolant:
     def _block_grids(parts):
         return {b: (i if fine is None else fine) for i, fine, _, b in parts}
 
-    def interpolate(self, yy, ml_samples_f):
+    def interpolate(self, yy, ml_samples_f, method=None):
         """Multilevel interpolant at the rows of ``yy``:
         I_0[s_K] + sum_{k=1}^{K} ( I_k[s_{K-k}] - I_{k-1}[s_{K-k} restricted] ), s = samples
-        (reference :103-114), in one fused launch.  Returns the squeezed (P, NF) array."""
+        (reference :103-114), in one fused launch.  Returns the squeezed (P, NF) array.
+        ``method``: "combination" (the reference's sum of combination formulas), "hierarchical"
+        (the work-reduced form, module docstring) or "auto" (default: the work-reduced form when
+        it exists, the batch has at least AUTO_MIN_POINTS rows and this call's validation
+        sample agrees with the exact launch to AUTO_TOL; outcome in ``auto_validation``)."""
+        from .sparse_grid_interpolant import DEFAULT_METHOD
+        method = DEFAULT_METHOD if method is None else method
+        if method not in ("auto", "combination", "hierarchical"):
+            raise ValueError("method must be 'auto', 'combination' or 'hierarchical'")
         K = self.n_levels - 1
         parts, blocks = [(0, None, 1.0, 0)], [ml_samples_f[K]]
         for k in range(1, self.n_levels):
             parts.append((k, None, 1.0, k))
             parts.append((k - 1, k, -1.0, k))
             blocks.append(ml_samples_f[K - k])
-        return self._evaluate(parts, blocks, yy, "raise")
+        return self._evaluate(parts, blocks, yy, "raise", method)
 
     def get_ml_terms(self, yy, ml_samples_f):
         """The multilevel terms one by one: entry k = (I_{K-k} - I_{K-k-1})[u_k], the last one

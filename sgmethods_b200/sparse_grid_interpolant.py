@@ -296,7 +296,8 @@ class SGInterpolant:
                                     "active direction")
 
     def hierarchical(self):
-        """The work-reduced evaluator (pw-linear, nested knots): see hierarchical.py."""
+        """The work-reduced evaluator (pw-linear, pw-quadratic or Lagrange operator on nested
+        knots): see hierarchical.py."""
         if getattr(self, "_hier", None) is None:
             from .hierarchical import HierarchicalPlan
             self._hier = HierarchicalPlan(self)
@@ -305,11 +306,11 @@ class SGInterpolant:
     # --------------------------------------------------------------- method selection
     def _auto_candidate(self, host_rows):
         """The hierarchical plan if ``method="auto"`` may use it for a batch of ``host_rows``
-        points, else None: the form exists for pw-linear operators on nested knots only
-        (hierarchical.py), small batches stay on the exact kernels (they are latency-bound
+        points, else None: the form exists for the pw-linear, pw-quadratic and Lagrange
+        operators on nested knots (hierarchical.py; not for pw-cubic), small batches stay on the exact kernels (they are latency-bound
         either way and the exact path is bit-identical), and an interpolant on which the form
         once failed its validation keeps the exact kernels."""
-        if self._kind != _lib.KIND_LINEAR or host_rows < AUTO_MIN_POINTS or \
+        if self._kind == _lib.KIND_CUBIC or host_rows < AUTO_MIN_POINTS or \
                 getattr(self, "_auto_choice", None) == "combination":
             return None
         try:
@@ -333,8 +334,12 @@ class SGInterpolant:
             xs = xs[:, :self.N].contiguous()
         exact = self.device_plan(device.index).eval(xs, f)
         fast = hp._dev(device.index)[0].eval(xs, alpha)
-        scale = exact.abs().max()
-        dev = (fast - exact).abs().max() / torch.where(scale > 0, scale, torch.ones_like(scale))
+        # NaN where the reference is NaN (Lagrange on a knot) counts as agreement; NaN in one of
+        # the two only poisons the maximum and fails the validation
+        both_nan = exact.isnan() & fast.isnan()
+        scale = torch.where(both_nan, torch.zeros_like(exact), exact.abs()).max()
+        dev = torch.where(both_nan, torch.zeros_like(exact), (fast - exact).abs()).max() / \
+            torch.where(scale > 0, scale, torch.ones_like(scale))
         host = getattr(self, "_auto_host", None)
         if host is None:
             host = self._auto_host = torch.empty(1, dtype=torch.float64).pin_memory()
@@ -362,9 +367,10 @@ class SGInterpolant:
         ``method``:
           * ``"combination"`` -- the reference's combination formula, bit for bit
             (sparse_grid_interpolant.py:268-279 with the operators' own arithmetic order);
-          * ``"hierarchical"`` -- the work-reduced hierarchical-surplus form (pw-linear, nested
-            knots; hierarchical.py): the same function with ~10x fewer gathers, agreeing with
-            the reference to about the reference's own rounding error;
+          * ``"hierarchical"`` -- the work-reduced hierarchical-surplus form (pw-linear,
+            pw-quadratic, Lagrange; nested knots; hierarchical.py): the same function with ~10x
+            fewer gathers, agreeing with the reference to about the reference's own rounding
+            error;
           * ``"auto"`` (the default, ``DEFAULT_METHOD``) -- the hierarchical form when it exists,
             the batch is large and THIS call's validation passes: a sample of the batch is
             evaluated by both kernels with the caller's nodal values and must agree to
@@ -424,7 +430,12 @@ class SGInterpolant:
             out = plan.eval(x, f_eval)           # enqueued before the verdict is read: it overlaps
             if pending is not None and not self._auto_verdict(*pending):
                 out = exact_plan.eval(x, f, out)             # validation failed: the exact kernel
-        if self._kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
+        flags = 0
+        if self._kind == _lib.KIND_QUADRATIC:
+            flags = plan.take_flags()
+            if hp is not None:               # the validation sample went through the exact plan
+                flags |= exact_plan.take_flags()
+        if flags & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot "
                              "(or is NaN); the reference raises IndexError here "
                              "(tp_inteprolants.py:131-133)")

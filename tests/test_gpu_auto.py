@@ -173,14 +173,14 @@ def test_auto_keeps_the_exact_kernel_when_the_form_does_not_exist_or_fails_valid
     x = rng.uniform(-1, 1, (20000, 4))
     assert np.array_equal(it.interpolate(x, f), it.interpolate(x, f, method="combination"))
     assert it.auto_validation["enabled"] is False
-    # other operators: never
-    from sgmethods_b200.tp_inteprolants import TPPwQuadraticInterpolator
-    itq = SGInterpolant(mis.smolyak_mid_set(2, 3), nodes_1d.cc_nodes,
-                        lambda n: np.where(n == 0, 1, 2 ** n + 1),
-                        tp_interpolant=TPPwQuadraticInterpolator, verbose=False)
+    # pw-cubic: never (its patches are not nested, hierarchical.py)
+    from sgmethods_b200.tp_inteprolants import TPPwCubicInterpolator
+    itq = SGInterpolant(mis.smolyak_mid_set(2, 3), nodes_1d.cc_nodes, lambda n: 3 * 2 ** n + 1,
+                        tp_interpolant=TPPwCubicInterpolator, verbose=False)
     fq = rng.normal(size=(itq.num_nodes, 1))
     xq = rng.uniform(-1, 1, (20000, 3))
     assert np.array_equal(itq.interpolate(xq, fq), itq.interpolate(xq, fq, method="combination"))
+    assert getattr(itq, "_hier", None) is None
     # a validation that fails (tolerance forced to 0) leaves the exact kernel in place
     it2 = config2(2)
     monkeypatch.setattr(sgi, "AUTO_TOL", 0.0)
@@ -218,3 +218,172 @@ def test_hierarchical_nan_and_ragged_batches():
         fast = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(P, 3)
         exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(P, 3)
         assert rel_dev(fast, exact) <= TOL
+
+
+# ------------------------------------------------------------ pw-quadratic and Lagrange
+DBL = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa: E731
+NO_FORM = {"lag_example0": "lev2knots(0) = 3", "lag_hermite": "Gauss-Hermite knots are not nested"}
+
+
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c[2] in ("quadratic", "lagrange")))
+def test_hierarchical_form_of_quadratic_and_lagrange_on_reference_outputs(name):
+    """The pw-quadratic and Lagrange fixtures: where the hierarchical form exists it reproduces
+    the REFERENCE's output to 1e-12, otherwise it says so and the exact kernel answers."""
+    from sgmethods_b200 import tp_inteprolants as tpi
+    fam, l2k, kind = CASES[name]
+    op = {"quadratic": tpi.TPPwQuadraticInterpolator, "lagrange": tpi.TPLagrangeInterpolator}[kind]
+    g = load_golden(name)
+    it = SGInterpolant(g["mid_set"], knot_family(fam, nodes_1d), LEV2KNOTS[l2k], tp_interpolant=op,
+                       verbose=False)
+    if name in NO_FORM:
+        with pytest.raises(NotImplementedError):
+            it.interpolate(g["x"], g["f_on_SG"], method="hierarchical")
+        out = it.interpolate(g["x"], g["f_on_SG"])
+    else:
+        out = it.interpolate(g["x"], g["f_on_SG"], method="hierarchical")
+        print(f"{name}: hierarchical vs reference output {rel_dev(out, g['out']):.2e}")
+    assert rel_dev(out, g["out"]) <= TOL
+
+
+def config4_level(k=3, d=8):
+    from sgmethods_b200.tp_inteprolants import TPPwQuadraticInterpolator
+    return SGInterpolant(mis.smolyak_mid_set(k, d), nodes_1d.cc_nodes, DBL,
+                         tp_interpolant=TPPwQuadraticInterpolator, verbose=False)
+
+
+@pytest.mark.parametrize("data", ["random", "smooth"])
+@pytest.mark.parametrize("NF", [1, 200])
+def test_config4_shape_quadratic_hierarchical_within_contract(data, NF):
+    """BASELINE config 4's finest level (pw-quadratic, d = 8, Smolyak level 3, Clenshaw-Curtis
+    knots 1, 3, 5, 9): 333 basis tuples instead of 165 terms x 3^k nodes."""
+    it = config4_level()
+    rng = np.random.default_rng(11)
+    f = rng.normal(size=(it.num_nodes, NF)) if data == "random" else smooth_values(it, NF)
+    x = rng.uniform(-1.2, 1.0, (20000 if NF == 1 else 9000, 8))       # left of the first knot too
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:64], f, kind="quadratic", squeeze=False)
+    fast = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(x.shape[0], NF)
+    exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(x.shape[0], NF)
+    assert np.array_equal(exact[:64], ref)
+    print(f"config-4 NF={NF} {data}: hierarchical vs reference arithmetic {rel_dev(fast, exact):.2e}")
+    assert rel_dev(fast[:64], ref) <= TOL and rel_dev(fast, exact) <= TOL
+    auto = np.asarray(it.interpolate(x, f)).reshape(x.shape[0], NF)
+    assert it.auto_validation["enabled"] and np.array_equal(auto, fast)
+
+
+def test_quadratic_hierarchical_raises_like_the_reference_right_of_the_last_knot():
+    it = config4_level(2, 3)
+    rng = np.random.default_rng(12)
+    f = rng.normal(size=(it.num_nodes, 1))
+    x = rng.uniform(-1, 1, (9000, 3))
+    it.interpolate(x, f, method="hierarchical")
+    x[4321, 1] = 1.0 + 1e-9                               # reference: IndexError (tp_inteprolants.py:131)
+    for method in ("hierarchical", "auto", "combination"):
+        with pytest.raises(IndexError):
+            it.interpolate(x, f, method=method)
+    x[4321, 1] = 1.0                                      # the last knot itself is fine
+    assert rel_dev(it.interpolate(x, f, method="hierarchical"), it.interpolate(x, f, method="combination")) <= TOL
+
+
+def leja_config2(w=4, d=16):
+    from sgmethods_b200.tp_inteprolants import TPLagrangeInterpolator
+    return SGInterpolant(mis.smolyak_mid_set(w, d), knot_family("leja", nodes_1d), lambda nu: nu + 1,
+                         tp_interpolant=TPLagrangeInterpolator, verbose=False)
+
+
+@pytest.mark.parametrize("data", ["random", "smooth"])
+def test_config2_leja_lagrange_hierarchical_within_contract(data):
+    """BASELINE config 2 as worded (Gaussian-Leja knots, d = 16, Lagrange): one Newton-like
+    basis polynomial per level, 4845 instead of 58 905 node contributions per point."""
+    it = leja_config2()
+    rng = np.random.default_rng(13)
+    f = rng.normal(size=(it.num_nodes, 1)) if data == "random" else smooth_values(it)
+    x = rng.normal(size=(30000, 16))
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:32], f, kind="lagrange")
+    fast = it.interpolate(x, f, method="hierarchical")
+    exact = it.interpolate(x, f, method="combination")
+    print(f"config-2 Leja {data}: hierarchical vs reference arithmetic {rel_dev(fast, exact):.2e}, "
+          f"exact vs oracle {rel_dev(exact[:32], ref):.2e}")
+    assert rel_dev(exact[:32], ref) <= TOL
+    assert rel_dev(fast[:32], ref) <= TOL and rel_dev(fast, exact) <= TOL
+    auto = it.interpolate(x, f)
+    # smooth values: the reference's own cancellation error is ~1e-13 here, so the per-call
+    # validation (2.5e-13 on its sample) may keep the exact kernel; either way inside 1e-12
+    print(f"config-2 Leja {data}: {it.auto_validation}")
+    if data == "random":
+        assert it.auto_validation["enabled"]
+    assert np.array_equal(auto, fast if it.auto_validation["enabled"] else exact)
+
+
+def test_lagrange_hierarchical_nan_on_knots_like_the_reference():
+    """A coordinate equal to a knot of an active direction: NaN in the reference
+    (tp_inteprolants.py:346, 0/0), NaN here, and method='auto' still validates (NaN == NaN)."""
+    it = leja_config2(3, 6)
+    rng = np.random.default_rng(14)
+    f = rng.normal(size=(it.num_nodes, 2))
+    x = rng.normal(size=(10000, 6))
+    knots = knot_family("leja", nodes_1d)(4)
+    x[0, 2], x[17, 5], x[9000, 0] = 0.0, knots[-1], knots[1]
+    ref = sg_oracle.interpolate(oracle_plan_of(it), x[:32], f, kind="lagrange", squeeze=False)
+    assert np.isnan(ref[0]).all() and np.isnan(ref[17]).all() and not np.isnan(ref[1]).any()
+    fast = it.interpolate(x, f, method="hierarchical")
+    exact = it.interpolate(x, f, method="combination")
+    assert np.isnan(fast[9000]).all() and np.isnan(exact[9000]).all()
+    assert rel_dev(fast[:32], ref) <= TOL and rel_dev(fast, exact) <= TOL      # rel_dev compares the NaN masks
+    xs = x.copy()
+    xs[::39, 3] = knots[2]                                # the validation sample sees NaNs as well
+    auto = it.interpolate(xs, f)
+    assert it.auto_validation["enabled"]
+    assert rel_dev(auto, it.interpolate(xs, f, method="combination")) <= TOL
+
+
+# ------------------------------------------------------------ multilevel (config 4)
+@pytest.mark.parametrize("name", ["ml_lin_nf1", "ml_quad_nf3", "ml_lin_grow"])
+def test_multilevel_hierarchical_form_on_reference_driver_outputs(name):
+    """MLInterpolant.interpolate in hierarchical-surplus form against the outputs of the
+    reference's own driver code (tests/golden/ml_*.npz), 1e-12."""
+    from golden_cases import ML_CASES, ml_mid_set
+    from sgmethods_b200 import tp_inteprolants as tpi
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    fam, l2k, kind, levels, NF, P, seed = ML_CASES[name]
+    op = {"linear": tpi.TPPwLinearInterpolator, "quadratic": tpi.TPPwQuadraticInterpolator}[kind]
+    g = load_golden(name)
+    seq = [SGInterpolant(np.asarray(ml_mid_set(mis, name, k)), knot_family(fam, nodes_1d),
+                         LEV2KNOTS[l2k], tp_interpolant=op, verbose=False) for k in range(levels)]
+    mli = MLInterpolant(seq)
+    ml = [g[f"ml_{k}"] for k in range(levels)]
+    out = mli.interpolate(g["yy"], ml, method="hierarchical")
+    assert out.shape == g["out"].shape
+    print(f"{name}: hierarchical multilevel vs reference driver output {rel_dev(out, g['out']):.2e}")
+    assert rel_dev(out, g["out"]) <= TOL
+    assert rel_dev(mli.interpolate(g["yy"], ml), g["out"]) <= TOL          # small batch: exact launch
+    assert rel_dev(mli.interpolate(g["yy"], ml, method="combination"), g["out"]) <= TOL
+
+
+def test_config4_shape_multilevel_auto_within_contract():
+    """BASELINE config 4: 4 levels, pw-quadratic, d = 8.  method='auto' evaluates ONE hierarchical
+    plan of 705 basis tuples whose surpluses come from the four sample blocks."""
+    from oracle import drivers_oracle
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    seq = [config4_level(k) for k in range(4)]
+    mli = MLInterpolant(seq)
+    rng = np.random.default_rng(15)
+    NF = 40
+    w = 1.0 / np.arange(1, 9) ** 2
+    ml = [np.stack([np.sin(seq[3 - k].SG @ w + 0.3 * c) + 2.0 ** (-2 * k) * np.cos(seq[3 - k].SG @ w * (c + 1))
+                    for c in range(NF)], axis=1) for k in range(4)]
+    yy = rng.uniform(-1.1, 1.0, (12000, 8))
+    plans = [oracle_plan_of(it) for it in seq]
+    for p, it in zip(plans, seq):
+        p.SG = it.SG
+    ref = drivers_oracle.ml_interpolate(plans, "quadratic", yy[:48], ml)
+    exact = mli.interpolate(yy, ml, method="combination")
+    auto = mli.interpolate(yy, ml)
+    print(f"config-4 multilevel: {mli.auto_validation}, auto vs exact launch {rel_dev(auto, exact):.2e}")
+    assert mli.auto_validation["enabled"]
+    assert rel_dev(exact[:48], np.squeeze(ref)) <= TOL and rel_dev(auto[:48], np.squeeze(ref)) <= TOL
+    assert rel_dev(auto, exact) <= TOL
+    assert np.array_equal(auto, mli.interpolate(yy, ml, method="hierarchical"))
+    yy[77, 3] = 1.0 + 1e-9
+    for method in ("auto", "hierarchical", "combination"):
+        with pytest.raises(IndexError):
+            mli.interpolate(yy, ml, method=method)
