@@ -1645,15 +1645,28 @@ int sgm_lc_brownian(const double* tt, int64_t nt, const double* yy, int64_t P, i
         if (gy > 65535) { rows = (P + 65534) / 65535; gy = (P + rows - 1) / rows; }
         using LcKernel = void (*)(const double*, int64_t, const double*, int64_t, int, int64_t, double,
                                   double, const double*, int, double*, int64_t, int);
+        // contiguous, 16-byte aligned rows: the row groups travel by bulk asynchronous copies
+        // (dev knob SGM_LC_BULK=0: the cp.async flavour, for comparison)
+        static const bool bulk_off = [] { const char* v = std::getenv("SGM_LC_BULK"); return v && v[0] == '0'; }();
+        const bool bulk = !bulk_off && ldy == d && d % 2 == 0 && (reinterpret_cast<uintptr_t>(yy) & 15) == 0;
         // compile-time row length for the full dyadic sizes (d = 2^L <= 64)
-        LcKernel kern = L > 6 ? sgm::lc_brownian_tiles_kernel<12, 2, 2>
-                      : d == 64 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 64>
-                      : d == 32 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 32>
-                      : d == 16 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 16>
-                                : sgm::lc_brownian_tiles_kernel<6, 2, 3>;
-        if (lc_smem > 48 * 1024)
-            SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem));
-        kern<<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem, st>>>(tt, nt, yy, P, d, ldy, T, sqrtT,
+        LcKernel kern = bulk
+            ? (L > 8 ? sgm::lc_brownian_tiles_kernel<12, 2, 2, 0, true>
+               : L > 6 ? sgm::lc_brownian_tiles_kernel<8, 2, 2, 0, true>
+               : d == 64 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 64, true>
+               : d == 32 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 32, true>
+               : d == 16 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 16, true>
+                         : sgm::lc_brownian_tiles_kernel<6, 2, 3, 0, true>)
+            : (L > 8 ? sgm::lc_brownian_tiles_kernel<12, 2, 2>
+               : L > 6 ? sgm::lc_brownian_tiles_kernel<8, 2, 2>
+               : d == 64 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 64>
+               : d == 32 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 32>
+               : d == 16 ? sgm::lc_brownian_tiles_kernel<6, 2, 3, 16>
+                         : sgm::lc_brownian_tiles_kernel<6, 2, 3>);
+        const size_t lc_smem_total = lc_smem + (bulk ? 16 : 0);       // + two mbarriers
+        if (lc_smem_total > 48 * 1024)
+            SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem_total));
+        kern<<<dim3((unsigned)gx, (unsigned)gy), 256, lc_smem_total, st>>>(tt, nt, yy, P, d, ldy, T, sqrtT,
                                                                      level_scale, L, W, ldw, (int)rows);
     } else {
         const int64_t total = P * nt;

@@ -2146,7 +2146,7 @@ constexpr int LC_ROWS = 32;
 // DC: number of coefficients when known at compile time (64 = config 3), 0 = run-time `d_rt`:
 // with a constant row length all staging index arithmetic folds away and the coefficient
 // reads of the unrolled row loop address as per-thread register + immediate.
-template <int LMAX, int TPT, int BPS, int DC = 0>
+template <int LMAX, int TPT, int BPS, int DC = 0, bool BULK = false>
 __global__ void __launch_bounds__(256, BPS)
 lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
                          const double* __restrict__ yy, int64_t P, int d_rt, int64_t ldy, double T,
@@ -2204,9 +2204,32 @@ lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
         return c == 0 ? 1.0 : (lv < L ? __ldg(level_scale + lv) : 0.0);
     };
     const double my_scale = level_scale_of(st_c);              // column is fixed if step_c == 0
+    // BULK (contiguous rows, ldy == d): a row group is ONE contiguous chunk of the input, so one
+    // elected thread moves it with a single bulk asynchronous copy (cp.async.bulk, the 1-D TMA
+    // path; completion counted in bytes on an mbarrier per buffer) instead of 256 threads
+    // issuing 8-byte cp.async each: no per-element address arithmetic, no LSU issue slots.
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(sy + 2 * (size_t)group_elems);
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     auto issue_copy = [&](int64_t pb, int buf) {
         const int nrows = (int)min((int64_t)LC_ROWS, p1 - pb);
         const unsigned dst0 = (unsigned)__cvta_generic_to_shared(sy + (size_t)buf * group_elems);
+        if (BULK) {
+            if (threadIdx.x == 0) {
+                const unsigned bytes = (unsigned)(nrows * d) * 8u;
+                const unsigned bar = mbar0 + 8u * (unsigned)buf;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst0), "l"(yy + pb * ldy), "r"(bytes), "r"(bar) : "memory");
+            }
+            return;
+        }
         // (row, column) of element i = threadIdx.x + 256 n, advanced without a division
         for (int i = threadIdx.x, r = st_r, c = st_c; i < nrows * d; i += 256) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst0 + 8u * i),
@@ -2222,13 +2245,24 @@ lc_brownian_tiles_kernel(const double* __restrict__ tt, int64_t nt,
     for (int64_t pb = p0; pb < p1; pb += LC_ROWS, ++g) {
         const int nrows = (int)min((int64_t)LC_ROWS, p1 - pb);
         double* buf = sy + (size_t)(g & 1) * group_elems;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (BULK) {
+            const unsigned bar = mbar0 + 8u * (unsigned)(g & 1), parity = (unsigned)(g >> 1) & 1u;
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         for (int i = threadIdx.x, c = st_c; i < nrows * d; i += 256) {
             const double sc = step_c == 0 ? my_scale : level_scale_of(c);
             if (c != 0) buf[i] = buf[i] * sc;                  // entry 0 stays y_0
             c += step_c;
             if (c >= d) c -= d;
         }
+        // BULK: order this thread's generic-proxy accesses to the buffers (reads of group g - 1,
+        // the scaling writes above) before the asynchronous-proxy write of the next copy
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();     // group g visible to all; everybody is done with group g - 1
         if (pb + LC_ROWS < p1) issue_copy(pb + LC_ROWS, (g + 1) & 1);
         // row pointers advance by uniform increments (shared-memory reads address as

@@ -8,7 +8,9 @@ The path shards naturally:
     nodal values.  There is no data-path collective; the only exchange is the optional final
     gather of the (P/G, NF) output slabs (``gather="all"`` -> NCCL all-gather,
     ``gather="root"`` -> gather to rank 0, ``gather=None`` -> the result stays sharded).
-    Results are bit-identical to the single-GPU run.
+    Results are bit-identical to the single-GPU run with the same ``method`` (the exact
+    kernels and the hierarchical kernels both compute a point's value independently of the
+    batch it is in, with a fixed summation order).
   * ``mode="terms"``: for few points and a huge combination set each rank evaluates a
     contiguous range of terms (balanced by corner count, reference order inside the range)
     at all points and the (P, NF) partial sums are combined with an NCCL all-reduce.  This
@@ -40,12 +42,16 @@ def balanced_term_ranges(cost, world):
 class ShardedInterpolant:
     """Evaluate ``interpolant`` (an SGInterpolant) on all ranks of a process group."""
 
-    def __init__(self, interpolant, group=None, mode="points", _evaluator=None):
+    def __init__(self, interpolant, group=None, mode="points", _evaluator=None, method=None):
+        """``method``: as in ``SGInterpolant.interpolate`` (points mode; None = its default,
+        the validated work-reduced form); the term-sharded mode always evaluates the
+        combination formula."""
         import torch.distributed as dist
         assert mode in ("points", "terms")
         self.it = interpolant
         self.group = group
         self.mode = mode
+        self.method = method
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # test hook: a callable (x, f, t0, t1) -> (P, NF) tensor standing in for the CUDA
@@ -65,11 +71,10 @@ class ShardedInterpolant:
     def _eval(self, x, f, t0=None, t1=None):
         if self._evaluator is not None:
             return self._evaluator(x, f, t0, t1)
-        import torch
         if t0 is None:
-            plan = self.it.device_plan(x.device.index)
-        else:
-            plan = self._terms_plan(x.device.index, t0, t1)
+            out = self.it.interpolate(x, f, method=self.method)     # all checks inside
+            return out.reshape(x.shape[0], f.shape[1])
+        plan = self._terms_plan(x.device.index, t0, t1)
         # same checks as SGInterpolant.interpolate: operator constraints before the launch, the
         # row count of f against the grid, the pw-quadratic condition flag after it
         self.it._check_operator_constraints()

@@ -32,6 +32,10 @@ cases = [("c3 w=10 exact", c3, c3.device_plan(0), None, "normal"),
          ("c4 lvl3 quadratic", c4, c4.device_plan(0), None, "uniform")]
 hp = c3.hierarchical()
 cases.append(("c3 w=10 hierarchical", c3, hp._dev(0)[0], hp, "normal"))
+hp4 = c4.hierarchical()
+cases.append(("c4 lvl3 hierarchical", c4, hp4._dev(0)[0], hp4, "uniform"))
+if len(sys.argv) > 1:
+    cases = [c for c in cases if c[0].startswith(sys.argv[1])]
 for name, it, plan, hier, sampler in cases:
     gen = torch.Generator(device=dev).manual_seed(0)
     for NF in (1000, 4096):
