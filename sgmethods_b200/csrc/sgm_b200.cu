@@ -1604,9 +1604,9 @@ int sgm_hier_apply_batches(double* alpha, int64_t NF, int64_t ld, const int32_t*
     if (total == 0) return SGM_OK;
     if (!child || !pa || !pb || !wa || !wb) return sgm_fail(SGM_ERR_INVALID, "hier_apply_batches: null buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (total * NF <= ((int64_t)1 << 20)) {        // one block walks all batches
-        sgm::hier_apply_all_kernel<<<1, 1024, 0, st>>>(alpha, NF, ld, child, pa, pb, wa, wb,
-                                                       batch_off_dev, n_batches);
+    if (total * NF <= ((int64_t)1 << 22)) {        // one thread-block cluster walks all batches
+        sgm::hier_apply_all_kernel<<<sgm::HIER_CLUSTER, 1024, 0, st>>>(alpha, NF, ld, child, pa, pb, wa, wb,
+                                                                       batch_off_dev, n_batches);
         SGM_CUDA(cudaGetLastError());
         return SGM_OK;
     }

@@ -2079,25 +2079,32 @@ __global__ void hier_apply_kernel(double* __restrict__ alpha, int64_t NF, int64_
     }
 }
 
-// All hierarchisation batches in ONE launch of ONE block (small tables: the batches are
-// sequential, a block-wide barrier separates them; 64 launches of a few microseconds of work
-// each cost more than the work).
-__global__ void __launch_bounds__(1024)
+// All hierarchisation batches in ONE launch of ONE thread-block cluster (small tables: the
+// batches are sequential, a barrier separates them; 64 launches of a few microseconds of work
+// each cost more than the work).  8 CTAs x 1024 threads share every batch and meet at the
+// hardware cluster barrier (arrive.release / wait.acquire at cluster scope orders the global
+// writes of a batch before the reads of the next): config 2's 64 batches 0.33 -> 0.06 ms
+// against one block with __syncthreads.
+constexpr int HIER_CLUSTER = 8;
+__global__ void __cluster_dims__(HIER_CLUSTER, 1, 1) __launch_bounds__(1024)
 hier_apply_all_kernel(double* __restrict__ alpha, int64_t NF, int64_t ld,
                       const int* __restrict__ child, const int* __restrict__ pa,
                       const int* __restrict__ pb, const double* __restrict__ wa,
                       const double* __restrict__ wb, const int64_t* __restrict__ batch_off,
                       int n_batches) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int b = 0; b < n_batches; ++b) {
         const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
         const int64_t total = n * NF;
-        for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        for (int64_t i = tid; i < total; i += nthreads) {
             const int64_t it = lo + i / NF, c = i % NF;
             double coarse = wa[it] * alpha[(int64_t)pa[it] * ld + c];
             if (pb[it] >= 0) coarse = coarse + wb[it] * alpha[(int64_t)pb[it] * ld + c];
             alpha[(int64_t)child[it] * ld + c] -= coarse;
         }
-        __syncthreads();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                     "barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
 
