@@ -63,7 +63,7 @@ struct Knobs {
     int prefix_run = 8;          // SGM_PREFIX_RUN
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
-    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false;
+    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, no_key2 = false;
     bool no_jit = false;         // SGM_NO_JIT: never build the plan-specialised small-plan kernel
     bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
     long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
@@ -83,6 +83,7 @@ struct Knobs {
         k.no_idx8 = std::getenv("SGM_NO_IDX8") != nullptr;
         k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
+        k.no_key2 = std::getenv("SGM_NO_KEY2") != nullptr;
         k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
         k.no_jit = std::getenv("SGM_NO_JIT") != nullptr;
         k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
@@ -105,6 +106,7 @@ struct sgm_plan {
     int64_t corners = 0;         // sum_t C_t
     bool all_packed = false;     // every term has a packed record (needed by the H1 kernel)
     bool prefix_ok = false;      // tables of the prefix kernel (pw-linear, all packed) are built
+    int first_level_keys = 0;    // directions in the locality key (before second-level bits)
     int prefix_wins = 0;         // occupancy comparison prefix vs split kernel (plan creation)
     bool prefix_launch_ok = false;
     bool h2_ok = false;          // tables of the grouped hierarchical kernel are built
@@ -663,8 +665,8 @@ int launch_cols_wide2(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, c
     return SGM_OK;
 }
 
-// Four points per warp on 128-column tiles (kernel C4); same contract as launch_cols_wide2.
-template <int KIND>
+// Four points per warp (kernel C4) on 64 * CPL2-column tiles; same contract as launch_cols_wide2.
+template <int KIND, int CPL2 = 2>
 int launch_cols_wide4(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                       int64_t ldf, int64_t ncols, double* out, int64_t ldo, double scale,
                       int accumulate, const int* perm, cudaStream_t stream, bool* launched) {
@@ -676,10 +678,10 @@ int launch_cols_wide4(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, c
     const size_t smem = fixed + per_warp * warps + 16;
     if (smem > (size_t)plan->max_smem_optin / 2) return SGM_OK;    // keep two blocks per SM
     const int quads_per_block = warps * 4;
-    const int64_t n_tiles = (ncols + 127) / 128;
+    const int64_t n_tiles = (ncols + 64 * CPL2 - 1) / (64 * CPL2);
     const int64_t gx = ((P + 3) / 4 + quads_per_block - 1) / quads_per_block;
     if (gx > 0x7fffffff || n_tiles > 65535) return SGM_OK;
-    auto kern = sgm::eval_cols_wide4_kernel<KIND, 2>;
+    auto kern = sgm::eval_cols_wide4_kernel<KIND, CPL2>;
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
         plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, quads_per_block, perm, ncols);
@@ -713,6 +715,15 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
             if (plan->knobs.wide_pts == 4 && NF >= 128) {
                 int rc4 = launch_cols_wide4<KIND>(plan, x, P, ldx, f, ldf, even, out, ldo, scale, accumulate, perm, stream, &launched);
                 if (rc4) return rc4;
+            }
+            if constexpr (KIND == SGM_HIER_PW_LINEAR) {
+                // hierarchical kind: one accumulator set per point (no per-term partial sums), so
+                // four points fit on 256-column tiles (default for plans with at most 8 keyed directions: config 4 x1.07-1.16, config 3 (d = 64) x1.0; dev knob SGM_WIDE_PTS=8 forces it, =2 the pair kernel)
+                const bool low_dim = plan->first_level_keys <= 8;     // neighbours share nearly all rows
+                if ((plan->knobs.wide_pts == 8 || (plan->knobs.wide_pts == 0 && low_dim)) && NF >= 256) {
+                    int rc4 = launch_cols_wide4<KIND, 4>(plan, x, P, ldx, f, ldf, even, out, ldo, scale, accumulate, perm, stream, &launched);
+                    if (rc4) return rc4;
+                }
             }
             int rc2 = launched ? SGM_OK : tile == 256
                 ? launch_cols_wide2<KIND, 4>(plan, x, P, ldx, f, ldf, nt2, even, out, ldo, scale, accumulate, perm, stream, &launched)
@@ -1255,12 +1266,14 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     {   // locality key: the (up to 16) most used directions, threshold = middle knot of the
         // smallest knot family with an interior knot used in that direction
         std::vector<int64_t> usage(N, 0);
-        std::vector<int> small_fam(N, -1);
+        std::vector<int> small_fam(N, -1), second_fam(N, -1);
         for (const TermDim& td : tdim) {
             const Entry& e = entries[td.ent];
             ++usage[e.dim];
             if (e.n >= 3 && (small_fam[e.dim] < 0 || e.n < entries[small_fam[e.dim]].n))
                 small_fam[e.dim] = td.ent;
+            if (e.n >= 5 && (second_fam[e.dim] < 0 || e.n < entries[second_fam[e.dim]].n))
+                second_fam[e.dim] = td.ent;
         }
         std::vector<int> order;
         for (int n = 0; n < N; ++n) if (small_fam[n] >= 0) order.push_back(n);
@@ -1275,10 +1288,32 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
             return usage[a] != usage[b] ? usage[a] > usage[b] : a > b;
         });
+        for (int i = 0; i < 16; ++i) d.key_dep[i] = -1;
         for (int i = 0; i < d.n_key; ++i) {
             const Entry& e = entries[small_fam[order[i]]];
             d.key_dim[i] = e.dim;
             d.key_thr[i] = desc->fam_knots[e.knot_off + e.n / 2];
+        }
+        // spare key bits (plans with fewer than 16 keyed directions, e.g. config 4 with d = 8):
+        // a second level per direction, most used first -- the quarter knots of the smallest
+        // family with at least 5 knots, chosen by the direction's first-level bit.  Points of one
+        // bin then share their brackets / patches two levels deep.
+        const int first_level = d.n_key;
+        plan->first_level_keys = first_level;
+        if (!plan->knobs.no_key2) {
+            std::vector<int> second;
+            for (int i = 0; i < first_level && first_level + (int)second.size() < 16; ++i)
+                if (second_fam[order[i]] >= 0) second.push_back(i);
+            const int total = first_level + (int)second.size();
+            for (size_t j = 0; j < second.size(); ++j) {
+                const int i = second[j], slot = first_level + (int)j;
+                const Entry& e = entries[second_fam[order[i]]];
+                d.key_dim[slot] = e.dim;
+                d.key_thr[slot] = desc->fam_knots[e.knot_off + e.n / 4];
+                d.key_thr2[slot] = desc->fam_knots[e.knot_off + (3 * e.n) / 4];
+                d.key_dep[slot] = (signed char)(total - 1 - i);       // bit position of entry i
+            }
+            d.n_key = total;
         }
     }
     std::vector<double> coeff(desc->coeffs, desc->coeffs + T);

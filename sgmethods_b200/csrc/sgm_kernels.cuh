@@ -87,9 +87,14 @@ struct PlanDev {
     int64_t seg_stride;
     // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
     // coarsest knot family used in that direction), for the n_key most used directions
+    // Plans with fewer than 16 keyed directions spend the spare bits on a SECOND level: entry i
+    // with key_dep[i] >= 0 tests the quarter knot of the half selected by the (more significant)
+    // key bit key_dep[i]: x >= (that bit ? key_thr2[i] : key_thr[i]).
     int n_key;
     int key_dim[16];
     double key_thr[16];
+    double key_thr2[16];
+    signed char key_dep[16];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -1309,8 +1314,11 @@ __device__ __forceinline__ unsigned locality_key(const PlanDev& pl, const double
     unsigned key = 0;
     // the most used direction is the most significant bit: neighbours in the sorted order then
     // differ in the least used directions first (matters when the bins are sparsely filled)
-    for (int i = 0; i < pl.n_key; ++i)
-        key |= (xp[pl.key_dim[i]] >= pl.key_thr[i] ? 1u : 0u) << (pl.n_key - 1 - i);
+    for (int i = 0; i < pl.n_key; ++i) {
+        const int dep = pl.key_dep[i];
+        const double thr = (dep >= 0 && ((key >> dep) & 1u)) ? pl.key_thr2[i] : pl.key_thr[i];
+        key |= (xp[pl.key_dim[i]] >= thr ? 1u : 0u) << (pl.n_key - 1 - i);
+    }
     return key;
 }
 __global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,

@@ -35,17 +35,17 @@ cases.append(("c3 w=10 hierarchical", c3, hp._dev(0)[0], hp, "normal"))
 hp4 = c4.hierarchical()
 cases.append(("c4 lvl3 hierarchical", c4, hp4._dev(0)[0], hp4, "uniform"))
 if len(sys.argv) > 1:
-    cases = [c for c in cases if c[0].startswith(sys.argv[1])]
+    cases = [c for c in cases if sys.argv[1] in c[0]]
 for name, it, plan, hier, sampler in cases:
     gen = torch.Generator(device=dev).manual_seed(0)
     for NF in (1000, 4096):
         f = torch.randn((it.num_nodes, NF), dtype=torch.float64, device=dev, generator=gen)
         fe = hier.surpluses(f) if hier is not None else f
-        for P in (16384, 100000):
+        for P in (16384, 100000) + ((1000000,) if name.startswith('c4') and NF == 1000 else ()):
             x = torch.randn((P, it.N), dtype=torch.float64, device=dev, generator=gen) if sampler == "normal" \
                 else torch.rand((P, it.N), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
             res, outs = {}, {}
-            for pts in ("2", "4"):
+            for pts in ("2", "4") + (("8",) if hier is not None else ()):
                 os.environ["SGM_WIDE_PTS"] = pts
                 plan.reload_knobs()
                 out = torch.empty((P, NF), dtype=torch.float64, device=dev)
@@ -53,6 +53,10 @@ for name, it, plan, hier, sampler in cases:
                 outs[pts] = out
             same = torch.equal(outs["2"], outs["4"])
             dev_rel = float((outs["2"] - outs["4"]).abs().max() / outs["2"].abs().max())
+            extra = ""
+            if "8" in res:
+                extra = (f"; 4 pts/warp x 256 columns {res['8']:.2f} ms (x{res['2'] / res['8']:.2f}) "
+                         f"identical={torch.equal(outs['2'], outs['8'])}")
             print(f"{name} P={P} NF={NF}: 2 pts/warp {res['2']:.2f} ms, 4 pts/warp {res['4']:.2f} ms "
-                  f"(x{res['2'] / res['4']:.2f}) identical={same} rel dev {dev_rel:.1e}", flush=True)
+                  f"(x{res['2'] / res['4']:.2f}) identical={same} rel dev {dev_rel:.1e}{extra}", flush=True)
             del outs
