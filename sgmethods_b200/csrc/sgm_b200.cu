@@ -366,7 +366,12 @@ void decide_prefix(sgm_plan* plan) {
     const PrefixLaunch L = choose_prefix_launch(plan);
     const SplitLaunch S = choose_split_launch<SGM_PW_LINEAR>(plan);
     plan->prefix_launch_ok = L.warps > 0;
-    plan->prefix_wins = L.warps > 0 && 4 * L.warps * L.blocks_per_sm >= 3 * S.warps * S.blocks_per_sm;
+    // measured: config 2 (64 table entries; prefix 3 x 8 warps, split 5 x 8 at 47 registers)
+    // prefix 25 ms, split 34 ms per 10^6 points; config 5 (288 entries; prefix 1 x 8 warps, split
+    // 2 x 16) prefix 110 ms, split 53 ms per 10^5.  The prefix kernel needs two resident blocks
+    // and at least half the split kernel's resident warps.
+    plan->prefix_wins = L.warps > 0 && L.blocks_per_sm >= 2 &&
+                        2 * L.warps * L.blocks_per_sm >= S.warps * S.blocks_per_sm;
 }
 
 // Kernel A0: few packed pw-linear terms, many points (gathers its node values itself).
