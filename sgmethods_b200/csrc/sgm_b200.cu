@@ -63,7 +63,7 @@ struct Knobs {
     int prefix_run = 8;          // SGM_PREFIX_RUN
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
-    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, no_key2 = false;
+    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, no_key2 = false, wide_bulk = false;
     bool no_jit = false;         // SGM_NO_JIT: never build the plan-specialised small-plan kernel
     bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
     long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
@@ -84,6 +84,7 @@ struct Knobs {
         k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
         k.no_key2 = std::getenv("SGM_NO_KEY2") != nullptr;
+        k.wide_bulk = std::getenv("SGM_WIDE_BULK") != nullptr;
         k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
         k.no_jit = std::getenv("SGM_NO_JIT") != nullptr;
         k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
@@ -700,6 +701,29 @@ int launch_cols_narrow(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, 
                        int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale,
                        int accumulate, cudaStream_t stream);
 
+// EXPERIMENT (dev knob SGM_WIDE_BULK=1): hierarchical kind, row segments staged by bulk copies.
+int launch_cols_wide_bulk(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
+                          int64_t ldf, int64_t ncols, double* out, int64_t ldo, double scale,
+                          int accumulate, cudaStream_t stream, bool* launched) {
+    *launched = false;
+    const PlanDev& d = plan->dev;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * sgm::WIDE_BULK_STAGES * (2048 + 8) + (size_t)d.n_knots * 16 +
+                        (size_t)warps * ((size_t)d.B * 8 + (size_t)d.E * 4 + 32 * 4);
+    if (smem > (size_t)plan->max_smem_optin / 2) return SGM_OK;
+    const int64_t n_tiles = (ncols + 255) / 256;
+    const int pts_per_block = warps * cols_points_per_warp(plan, P, n_tiles, warps);
+    const int64_t gx = (P + pts_per_block - 1) / pts_per_block;
+    if (gx > 0x7fffffff || n_tiles > 65535) return SGM_OK;
+    auto kern = sgm::eval_cols_wide_bulk_kernel;
+    SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)gx, (unsigned)n_tiles), warps * 32, smem, stream>>>(
+        plan->dev, x, P, ldx, f, ldf, out, ldo, scale, accumulate, pts_per_block, ncols);
+    SGM_CUDA(cudaGetLastError());
+    *launched = true;
+    return SGM_OK;
+}
+
 template <int KIND>
 int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const double* f,
                 int64_t ldf, int64_t NF, double* out, int64_t ldo, double scale, int accumulate,
@@ -712,6 +736,18 @@ int launch_cols(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, const d
         const int tile = NF >= 512 ? 256 : (NF >= 128 ? 128 : 64);
         const int64_t n_tiles = NF / tile;
         bool launched = false;
+        if constexpr (KIND == SGM_HIER_PW_LINEAR) {
+            if (plan->knobs.wide_bulk && NF >= 256 && plan->dev.n_corners > 0) {
+                const int64_t even = NF & ~(int64_t)1;
+                int rcb = launch_cols_wide_bulk(plan, x, P, ldx, f, ldf, even, out, ldo, scale, accumulate, stream, &launched);
+                if (rcb) return rcb;
+                if (launched) {
+                    if (even == NF) return SGM_OK;
+                    return launch_cols_narrow<KIND>(plan, x, P, ldx, f + even, ldf, 1, out + even, ldo,
+                                                    scale, accumulate, stream);
+                }
+            }
+        }
         if (perm && plan->knobs.wide_pairs != 0) {
             // the pair kernel guards its last tile: all (even many) columns in one launch,
             // an odd last column through the guarded narrow kernel

@@ -1674,6 +1674,137 @@ eval_cols_wide_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
     }
 }
 
+// EXPERIMENT (BASELINE's "TMA-staged when NF is large", dev knob SGM_WIDE_BULK=1; rejected, see
+// DESIGN.md 7.1 and profiles/r2_cols_bulk_ncu_full.txt): the one-point-per-warp wide kernel of
+// the hierarchical kind with the 2 KB row segments staged in shared memory by bulk asynchronous
+// copies (cp.async.bulk 1-D, one mbarrier per stage, a ring of WIDE_BULK_STAGES stages per warp,
+// lane 0 of each warp is its producer) instead of per-lane LDG.128 through L1.  Same arithmetic
+// as eval_cols_wide_kernel<SGM_HIER, 4> (bit-identical).
+constexpr int WIDE_BULK_STAGES = 4;
+__global__ void __launch_bounds__(256)
+eval_cols_wide_bulk_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P, int64_t ldx,
+                           const double* __restrict__ f, int64_t ldf, double* __restrict__ out,
+                           int64_t ldo, double scale, int accumulate, int pts_per_block, int64_t ncols) {
+    constexpr int KIND = SGM_HIER_PW_LINEAR;
+    constexpr int CPL2 = 4, D = WIDE_BULK_STAGES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    // [ring: n_warps x D x 2 KB][mbarriers: n_warps x D][knots | lambda | basis tables | indices]
+    double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * D * 256;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(
+        smem_raw + (size_t)n_warps * D * 2048 + (size_t)warp * D * 8);
+    double* sknots = reinterpret_cast<double*>(smem_raw + (size_t)n_warps * D * 2048 + (size_t)n_warps * D * 8);
+    double* slambda = sknots + pl.n_knots;
+    for (int i = threadIdx.x; i < pl.n_knots; i += blockDim.x) {
+        sknots[i] = pl.knots[i];
+        slambda[i] = pl.lambda[i];
+    }
+    double* sbas_all = sknots + 2 * (size_t)pl.n_knots;
+    double* bas = sbas_all + (size_t)warp * pl.B;
+    int* idx = reinterpret_cast<int*>(sbas_all + (size_t)n_warps * pl.B) + (size_t)warp * pl.E;
+    int* srow = idx + (size_t)(n_warps - warp) * pl.E + (size_t)warp * 32;      // [n_warps][32] after the indices
+    if (lane == 0) {
+        for (int s = 0; s < D; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t colbase = (int64_t)blockIdx.y * 256;
+    const int tile_cols = (int)min((int64_t)256, ncols - colbase);           // even (launcher)
+    const unsigned tile_bytes = (unsigned)tile_cols * 8u;
+    const int64_t col0 = colbase + 2 * lane;
+    bool okc[CPL2];
+#pragma unroll
+    for (int c = 0; c < CPL2; ++c) okc[c] = 2 * lane + 64 * c + 1 < tile_cols;
+    unsigned n_issued = 0, n_used = 0;                    // entries issued / consumed by this warp so far
+    const int64_t p_begin = (int64_t)blockIdx.x * pts_per_block;
+    const int64_t p_end = min(P, p_begin + pts_per_block);
+    for (int64_t p = p_begin + warp; p < p_end; p += n_warps) {
+        const double* xp = x + p * ldx;
+        __syncwarp();
+        for (int e = lane; e < pl.E; e += 32) {
+            const Entry en = pl.ent[e];
+            fill_basis<KIND, int>(en, xp[en.dim], sknots, slambda, bas, idx, e, 1, pl.flags);
+        }
+        __syncwarp();
+        double2 acc[CPL2];
+#pragma unroll
+        for (int c = 0; c < CPL2; ++c) acc[c] = make_double2(0.0, 0.0);
+        for (int g0 = 0; g0 < pl.n_corners; g0 += 32) {
+            const int g = g0 + lane;
+            double w = 0.0;
+            int row = 0;
+            if (g < pl.n_corners) {
+                const int t = pl.corner_term[g];
+                const TermHdr h = pl.hdr[t];
+                const TermDim* td = pl.tdim + h.dim_off;
+                int off = 0;
+                w = pl.coeff[t];
+                for (int j = 0; j < h.k; ++j) {
+                    const TermDim d = td[j];
+                    w = w * bas[d.boff];
+                    off += idx[d.ent] * d.stride;
+                }
+                row = pl.maps[h.val_off + off];
+            }
+            __syncwarp();
+            srow[lane] = row;
+            __syncwarp();
+            const int n_in = min(32, pl.n_corners - g0);
+            auto issue = [&](int cc) {                      // lane 0: row of entry cc -> next stage
+                const unsigned s = n_issued % D;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(tile_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(ring0 + 2048u * s), "l"(f + (int64_t)srow[cc] * ldf + colbase), "r"(tile_bytes),
+                               "r"(bar0 + 8u * s) : "memory");
+            };
+            for (int i = 0; i < min(D - 1, n_in); ++i) {
+                if (lane == 0) issue(i);
+                ++n_issued;
+            }
+            for (int cc = 0; cc < n_in; ++cc) {
+                if (cc + D - 1 < n_in) {
+                    if (lane == 0) issue(cc + D - 1);
+                    ++n_issued;
+                }
+                const unsigned s = n_used % D, parity = (n_used / D) & 1u;
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar0 + 8u * s), "r"(parity) : "memory");
+                ++n_used;
+                const double wv = __shfl_sync(0xffffffffu, w, cc);
+                const double* seg = ring + (size_t)s * 256 + 2 * lane;
+#pragma unroll
+                for (int c = 0; c < CPL2; ++c) {
+                    const double2 v = okc[c] ? *reinterpret_cast<const double2*>(seg + 64 * c) : make_double2(0.0, 0.0);
+                    acc[c].x = fma(v.x, wv, acc[c].x);
+                    acc[c].y = fma(v.y, wv, acc[c].y);
+                }
+                __syncwarp();                               // stage s may be refilled from the next iteration on
+            }
+        }
+        double* o = out + p * ldo + col0;
+#pragma unroll
+        for (int c = 0; c < CPL2; ++c) {
+            if (!okc[c]) continue;
+            double2* dst = reinterpret_cast<double2*>(o + 64 * c);
+            double2 r = make_double2(scale * acc[c].x, scale * acc[c].y);
+            if (accumulate) {
+                const double2 old = *dst;
+                r.x = old.x + r.x;
+                r.y = old.y + r.y;
+            }
+            *dst = r;
+        }
+    }
+}
+
 // Kernel C3 ("wide pairs"): the wide kernel with TWO points per warp.  The points come in the
 // order of the locality permutation, so the two points of a warp mostly lie in the same
 // brackets of the coarse levels and their corner contributions read the SAME rows of f: a row
