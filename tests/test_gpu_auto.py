@@ -387,3 +387,34 @@ def test_config4_shape_multilevel_auto_within_contract():
     for method in ("auto", "hierarchical", "combination"):
         with pytest.raises(IndexError):
             mli.interpolate(yy, ml, method=method)
+
+
+# ------------------------------------------------------------ random downward closed sets
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("kind", ["linear", "quadratic", "lagrange"])
+def test_random_downward_closed_sets_hierarchical_kernels(kind, seed):
+    """Random (not Smolyak-shaped) downward closed sets, scalar and vector-valued: grouped
+    hierarchical kernel / hierarchical column kernels against the oracle (first rows) and the
+    exact CUDA path (all rows), 1e-12."""
+    from test_hierarchical_cpu import _random_downward_closed_set
+    from sgmethods_b200 import tp_inteprolants as tpi
+    rng = np.random.default_rng(200 + seed)
+    N = int(rng.integers(2, 7))
+    S = _random_downward_closed_set(rng, N, 4 if kind != "lagrange" else 3, int(rng.integers(10, 60)))
+    if kind == "linear":
+        op, knots, lev = tpi.TPPwLinearInterpolator, nodes_1d.unbounded_nodes_nested, L2K
+        x = rng.normal(0, 1.5, (9000, N))
+    elif kind == "quadratic":
+        op, knots, lev = tpi.TPPwQuadraticInterpolator, nodes_1d.cc_nodes, DBL
+        x = rng.uniform(-1.2, 1.0, (9000, N))
+    else:
+        op, knots, lev = tpi.TPLagrangeInterpolator, nodes_1d.cc_nodes, DBL
+        x = rng.uniform(-1.0, 1.0, (9000, N))
+    it = SGInterpolant(S, knots, lev, tp_interpolant=op, verbose=False)
+    for NF in (1, 130):
+        f = rng.normal(size=(it.num_nodes, NF))
+        ref = sg_oracle.interpolate(oracle_plan_of(it), x[:40], f, kind=kind, squeeze=False)
+        fast = np.asarray(it.interpolate(x, f, method="hierarchical")).reshape(-1, NF)
+        exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(-1, NF)
+        assert rel_dev(exact[:40], ref) <= TOL
+        assert rel_dev(fast[:40], ref) <= TOL and rel_dev(fast, exact) <= TOL

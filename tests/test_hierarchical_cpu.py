@@ -263,3 +263,52 @@ def test_multilevel_hierarchical_tables_reproduce_the_reference_driver_outputs(n
         out += alpha[top._maps_f[top._map_off[t] + off]] * w[:, None]
     ref = np.asarray(g["out"]).reshape(out.shape)
     assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def _random_downward_closed_set(rng, N, max_level, size):
+    """A random downward closed multi-index set, lexicographically sorted (what the
+    constructor requires): grown from the origin by admissible neighbours."""
+    members = {(0,) * N}
+    for _ in range(size * 4):
+        if len(members) >= size:
+            break
+        base = list(sorted(members)[rng.integers(len(members))])
+        d = int(rng.integers(N))
+        base[d] += 1
+        if base[d] > max_level:
+            continue
+        cand = tuple(base)
+        ok = all(tuple(cand[j] - (1 if j == i else 0) for j in range(N)) in members
+                 for i in range(N) if cand[i] > 0)
+        if ok:
+            members.add(cand)
+    return np.array(sorted(members), dtype=np.int64)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("kind", ["linear", "quadratic", "lagrange"])
+def test_random_downward_closed_sets_all_operators(kind, seed):
+    """Random (not Smolyak-shaped) downward closed sets: the hierarchical tables and the group
+    tables of the grouped kernel reproduce the oracle's combination formula to 1e-12."""
+    from sgmethods_b200 import tp_inteprolants as tpi
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.integers(2, 6))
+    S = _random_downward_closed_set(rng, N, 4 if kind != "lagrange" else 3, int(rng.integers(8, 40)))
+    if kind == "linear":
+        op, knots, lev = tpi.TPPwLinearInterpolator, nodes_1d.unbounded_nodes_nested, (lambda n: 2 ** (n + 1) - 1)
+        x = rng.normal(0, 1.5, (120, N))
+    elif kind == "quadratic":
+        op, knots, lev = tpi.TPPwQuadraticInterpolator, nodes_1d.cc_nodes, (lambda n: np.where(n == 0, 1, 2 ** n + 1))
+        x = rng.uniform(-1.2, 1.0, (120, N))
+    else:
+        op, knots, lev = tpi.TPLagrangeInterpolator, nodes_1d.cc_nodes, (lambda n: np.where(n == 0, 1, 2 ** n + 1))
+        x = rng.uniform(-1.0, 1.0, (120, N))
+    it = SGInterpolant(S, knots, lev, tp_interpolant=op, verbose=False)
+    hp = HierarchicalPlan(it)
+    f = rng.normal(size=(it.num_nodes, 2))
+    ref = sg_oracle.interpolate(
+        sg_oracle.plan_from_tables(it.N, it.combination_coeffs, it.active_tp_dims,
+                                   it.active_tp_nodes_list, it.map_tp_to_SG), x, f, squeeze=False, kind=kind)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(emulate(hp, x, f) - ref)) <= 1e-12 * scale
+    assert np.max(np.abs(emulate_groups(hp, x, f) - ref)) <= 1e-12 * scale
