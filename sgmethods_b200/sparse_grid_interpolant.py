@@ -230,11 +230,15 @@ class SGInterpolant:
                 device=device)
         return self._device_plans[device]
 
-    def _interpolate_pipelined(self, torch, plan, x_host, f, device):
+    def _interpolate_pipelined(self, torch, choose, x_host, NF, device, after=None):
         """Host points (pinned torch tensor, or numpy array staged through two pinned
         buffers): the chunks are copied on a side stream while the previous chunk is being
-        evaluated; the kernels stay on the current stream, in order."""
-        P, NF = x_host.shape[0], f.shape[1]
+        evaluated; the kernels stay on the current stream, in order.  ``choose()`` returns the
+        (plan, values) pair to evaluate with; it is called after the first copy has been
+        enqueued, so the verdict of method="auto"'s validation (a host synchronisation on two
+        small launches) overlaps the first host-to-device transfer."""
+        P = x_host.shape[0]
+        plan = f = None
         out = torch.empty((P, NF), dtype=torch.float64, device=device)
         compute = torch.cuda.current_stream(device)
         is_numpy = isinstance(x_host, np.ndarray)
@@ -260,7 +264,12 @@ class SGInterpolant:
                              for _ in range(2)]
         copier, dev_buf, dev_free = st["copier"], st["dev_buf"], st["dev_free"]
         staging, staging_free = st["staging"], st["staging_free"]
-        copier.wait_stream(compute)
+        # the copies wait for the work that was enqueued BEFORE this call (``after``, recorded at
+        # the top of interpolate()), not for this call's own validation launches
+        if after is not None:
+            copier.wait_event(after)
+        else:
+            copier.wait_stream(compute)
         for i, lo in enumerate(range(0, P, _H2D_CHUNK)):
             hi = min(P, lo + _H2D_CHUNK)
             b = i % 2
@@ -283,6 +292,8 @@ class SGInterpolant:
                 staging_free[b] = done
             # enqueue the evaluation of this chunk right away so that it overlaps the host
             # side staging copy of the next one
+            if plan is None:
+                plan, f = choose()
             compute.wait_event(done)
             plan.eval(xd, f, out[lo:hi])
             dev_free[b] = torch.cuda.Event()
@@ -400,6 +411,15 @@ class SGInterpolant:
         if host_rows and x_new.shape[1] < n_used:
             raise IndexError(f"x_new has {x_new.shape[1]} columns, the interpolant uses {n_used}")
         exact_plan = self.device_plan(device.index)
+        pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
+            x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
+        big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
+            x_new.dtype == np.float64 and x_new.shape[1] >= self.N
+        pipelined = (pinned or big_numpy) and host_rows >= 4 * _H2D_CHUNK
+        entry = None
+        if pipelined:
+            entry = torch.cuda.Event()
+            entry.record(torch.cuda.current_stream(device))
         plan, f_eval, pending = exact_plan, f, None
         hp = self.hierarchical() if method == "hierarchical" else \
             (self._auto_candidate(host_rows) if method == "auto" else None)
@@ -408,15 +428,13 @@ class SGInterpolant:
             f_eval = hp.surpluses(f[:hp.M])      # nodal values -> hierarchical surpluses (GPU)
             if method == "auto":
                 pending = self._auto_validation_launch(torch, hp, x_new, f, f_eval, device, host_rows)
-        pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
-            x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
-        big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
-            x_new.dtype == np.float64 and x_new.shape[1] >= self.N
-        if (pinned or big_numpy) and host_rows >= 4 * _H2D_CHUNK:
-            if pending is not None and not self._auto_verdict(*pending):
-                plan, f_eval = exact_plan, f
+        if pipelined:
+            def choose(pending=pending, plan=plan, f_eval=f_eval):
+                if pending is not None and not self._auto_verdict(*pending):
+                    return exact_plan, f
+                return plan, f_eval
             pending = None
-            out = self._interpolate_pipelined(torch, plan, x_new, f_eval, device)
+            out = self._interpolate_pipelined(torch, choose, x_new, f.shape[1], device, after=entry)
         else:
             if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):
                 x_new = x_new[:, :self.N]        # only the first N columns travel to the GPU
