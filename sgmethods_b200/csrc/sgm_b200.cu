@@ -64,6 +64,7 @@ struct Knobs {
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
     bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, no_key2 = false, wide_bulk = false;
+    int dev_flags = 0;           // SGM_DEV_FLAGS: PlanDev::dev_flags
     bool no_jit = false;         // SGM_NO_JIT: never build the plan-specialised small-plan kernel
     bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
     long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
@@ -85,6 +86,7 @@ struct Knobs {
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
         k.no_key2 = std::getenv("SGM_NO_KEY2") != nullptr;
         k.wide_bulk = std::getenv("SGM_WIDE_BULK") != nullptr;
+        if (const char* v = std::getenv("SGM_DEV_FLAGS")) k.dev_flags = std::atoi(v);
         k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
         k.no_jit = std::getenv("SGM_NO_JIT") != nullptr;
         k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
@@ -1290,6 +1292,7 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     sgm_plan* plan = new sgm_plan();
     plan->device = device;
     plan->knobs = Knobs::from_env();
+    plan->dev.dev_flags = plan->knobs.dev_flags;
     plan->M = desc->M;
     cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -1506,6 +1509,7 @@ int sgm_plan_reload_knobs(sgm_plan* plan) {
     if (!plan) return sgm_fail(SGM_ERR_INVALID, "reload_knobs: null plan");
     DeviceGuard guard(plan->device);
     plan->knobs = Knobs::from_env();
+    plan->dev.dev_flags = plan->knobs.dev_flags;
     decide_prefix(plan);
     return SGM_OK;
 }

@@ -90,6 +90,7 @@ struct PlanDev {
     // Plans with fewer than 16 keyed directions spend the spare bits on a SECOND level: entry i
     // with key_dep[i] >= 0 tests the quarter knot of the half selected by the (more significant)
     // key bit key_dep[i]: x >= (that bit ? key_thr2[i] : key_thr[i]).
+    int dev_flags;                     // development switches: 1 = strided entry fill, 2 = read all 7 member slots
     int n_key;
     int key_dim[16];
     double key_thr[16];
@@ -678,10 +679,20 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
         const int64_t p = perm ? (int64_t)perm[valid ? slot : P - 1] : (valid ? slot : P - 1);
         const double* xp = x + p * ldx;
         __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
-        for (int e = warp; e < pl.E; e += W) {
-            const Entry en = pl.ent[e];
-            fill_basis<KIND, IdxT>(en, xp[en.dim], sknots, slambda, bas_all + lane,
-                                   idx_all + lane, e, 32, pl.flags);
+        {   // every warp fills a run of CONSECUTIVE entries: the entries are numbered in order of
+            // first use, so a run mostly stays in one direction and reads its coordinate once
+            // (a per-lane row read costs the L1 data pipe 32 wavefronts)
+            const bool strided = pl.dev_flags & 1;
+            const int per = (pl.E + W - 1) / W;
+            int last_dim = -1;
+            double xv = 0.0;
+            for (int e = strided ? warp : warp * per; e < (strided ? pl.E : min(pl.E, (warp + 1) * per));
+                 e += strided ? W : 1) {
+                const Entry en = pl.ent[e];
+                if (en.dim != last_dim) { xv = xp[en.dim]; last_dim = en.dim; }
+                fill_basis<KIND, IdxT>(en, xv, sknots, slambda, bas_all + lane,
+                                       idx_all + lane, e, 32, pl.flags);
+            }
         }
         __syncthreads();
         if (pl.T == 0 && warp == 0 && valid) {
@@ -822,13 +833,27 @@ eval_points_prefix_kernel(const PlanDev pl, const double* __restrict__ x, int64_
             p[j] = perm ? (int64_t)perm[valid[j] ? slot : P - 1] : (valid[j] ? slot : P - 1);
         }
         __syncthreads();     // previous tile: nobody still reads the basis / knots are staged
-        for (int e = warp; e < pl.E; e += W) {
-            const Entry en = pl.ent[e];
+        {   // runs of consecutive entries per warp: one coordinate read per direction of the run
+            const bool strided = pl.dev_flags & 1;
+            const int per = (pl.E + W - 1) / W;
+            int last_dim = -1;
+            double xv[PPL];
 #pragma unroll
-            for (int j = 0; j < PPL; ++j)
-                fill_basis<SGM_PW_LINEAR, unsigned short>(en, x[p[j] * ldx + en.dim], sknots, nullptr,
-                                                          bas_all + lane + 32 * j,
-                                                          idx_all + lane + 32 * j, e, TPTS, pl.flags);
+            for (int j = 0; j < PPL; ++j) xv[j] = 0.0;
+            for (int e = strided ? warp : warp * per; e < (strided ? pl.E : min(pl.E, (warp + 1) * per));
+                 e += strided ? W : 1) {
+                const Entry en = pl.ent[e];
+                if (en.dim != last_dim) {
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) xv[j] = x[p[j] * ldx + en.dim];
+                    last_dim = en.dim;
+                }
+#pragma unroll
+                for (int j = 0; j < PPL; ++j)
+                    fill_basis<SGM_PW_LINEAR, unsigned short>(en, xv[j], sknots, nullptr,
+                                                              bas_all + lane + 32 * j,
+                                                              idx_all + lane + 32 * j, e, TPTS, pl.flags);
+            }
         }
         __syncthreads();
         if (T == 0 && warp == 0) {
@@ -1074,10 +1099,18 @@ eval_hier_points_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
         const int64_t p = perm ? (int64_t)perm[valid ? slot : P - 1] : (valid ? slot : P - 1);
         const double* xp = x + p * ldx;
         __syncthreads();
-        for (int e = warp; e < pl.E; e += W) {
-            const Entry en = pl.ent[e];
-            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
-                                             idx_all + lane, e, 32, pl.flags);
+        {   // runs of consecutive entries per warp: one coordinate read per direction of the run
+            const bool strided = pl.dev_flags & 1;
+            const int per = (pl.E + W - 1) / W;
+            int last_dim = -1;
+            double xv = 0.0;
+            for (int e = strided ? warp : warp * per; e < (strided ? pl.E : min(pl.E, (warp + 1) * per));
+                 e += strided ? W : 1) {
+                const Entry en = pl.ent[e];
+                if (en.dim != last_dim) { xv = xp[en.dim]; last_dim = en.dim; }
+                fill_basis<KIND, unsigned short>(en, xv, sknots, slambda, bas_all + lane,
+                                                 idx_all + lane, e, 32, pl.flags);
+            }
         }
         __syncthreads();
         // the multi-indices are grouped by their number k of active directions (the order of
@@ -1219,10 +1252,18 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
         const int64_t p = perm ? (int64_t)perm[valid ? slot_p : P - 1] : (valid ? slot_p : P - 1);
         const double* xp = x + p * ldx;
         __syncthreads();
-        for (int e = warp; e < pl.E; e += W) {
-            const Entry en = pl.ent[e];
-            fill_basis<KIND, unsigned short>(en, xp[en.dim], sknots, slambda, bas_all + lane,
-                                             idx_all + lane, e, 32, pl.flags);
+        {   // runs of consecutive entries per warp: one coordinate read per direction of the run
+            const bool strided = pl.dev_flags & 1;
+            const int per = (pl.E + W - 1) / W;
+            int last_dim = -1;
+            double xv = 0.0;
+            for (int e = strided ? warp : warp * per; e < (strided ? pl.E : min(pl.E, (warp + 1) * per));
+                 e += strided ? W : 1) {
+                const Entry en = pl.ent[e];
+                if (en.dim != last_dim) { xv = xp[en.dim]; last_dim = en.dim; }
+                fill_basis<KIND, unsigned short>(en, xv, sknots, slambda, bas_all + lane,
+                                                 idx_all + lane, e, 32, pl.flags);
+            }
         }
         for (int i = threadIdx.x; i < H2_LISTS * 32; i += blockDim.x) sAcc[i] = 0.0;
         if (threadIdx.x < H2_LISTS) sTicket[threadIdx.x] = 0;
@@ -1239,6 +1280,7 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             const int4 h1 = ldg_keep(gh + 1);// member entries * 64 (8 x u16; unused: the dummy entry)
             const int4 h2 = ldg_keep(gh + 2);// step bounds per member count (8 x u16)
             const int n_steps = h0.y & 0xffff, n_par = (h0.y >> 20) & 0xf;   // (bits 24..29: list)
+            const int n_mem = (pl.dev_flags & 2) ? 7 : (h0.y >> 16) & 0xf;
             double w_par = 1.0;
             int off_par = 0;
             {                                // the parent's path: entry * 64 | extent << 16 per word
@@ -1260,7 +1302,9 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
             for (int g = 0; g < 7; ++g) {
                 const unsigned e64 = (g & 1) ? me[g >> 1] >> 16 : me[g >> 1] & 0xffffu;
                 acc[g] = 0.0;
-                og[g] = off_par + h0.z * (int)*reinterpret_cast<const unsigned short*>(ibase + e64);
+                // unused member slots (group-uniform) skip their table reads: 3 wavefronts each
+                og[g] = g < n_mem ? off_par + h0.z * (int)*reinterpret_cast<const unsigned short*>(ibase + e64)
+                                  : off_par;
             }
             // steps are listed by decreasing number of present members; bound i = first step
             // (relative) with fewer than 7 - i members
@@ -1282,7 +1326,7 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 #pragma unroll
             for (int g = 0; g < 7; ++g) {
                 const unsigned e64 = (g & 1) ? me[g >> 1] >> 16 : me[g >> 1] & 0xffffu;
-                gsum = fma(*reinterpret_cast<const double*>(ybase + 4u * e64), acc[g], gsum);
+                if (g < n_mem) gsum = fma(*reinterpret_cast<const double*>(ybase + 4u * e64), acc[g], gsum);
             }
             {   // add to the group's list in list order (ticket = position in the list)
                 const int list = (h0.y >> 24) & 0x3f, pos = h2.w;
