@@ -119,6 +119,34 @@ def secondary_rooflines(P, corners, terms, kernel_ms, clk):
             "frac_of_l1_floor": t_l1 / t, "frac_of_fp64_floor": t_fp64 / t}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run this rank's host threads (and therefore first-touch its pinned
+    staging memory) on the CPU cores of the NUMA node its GPU hangs off, so that the N
+    simultaneous host-to-device copies of the e2e step do not cross the socket interconnect.
+    Returns a short description (or None when the topology files are not visible)."""
+    try:
+        if os.environ.get("SGM_BENCH_NO_NUMA"):
+            return None
+        pr = torch.cuda.get_device_properties(local_rank)
+        pci = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{pci}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        use = cpus & os.sched_getaffinity(0)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return f"gpu {pci}: {len(use)} local cores ({spec})"
+    except Exception:                                   # no sysfs / no permission: leave as is
+        return None
+
+
 def measured_fp64():
     """FP64 pipe rates measured on the box by tools/mb_fp64 (built by __graft_entry__.build();
     run live when the binary is there), else the committed record of the same binary
@@ -517,6 +545,7 @@ def main():
                          "for the CPU baseline")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peak, peak_src = measured_peak_gbs()
@@ -671,7 +700,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
                     "d2h_bytes_per_step": int(world * P * NF * 8), "steps": e2e_steps,
-                    "includes_final_gather_to_rank0": world > 1},
+                    "includes_final_gather_to_rank0": world > 1, "host_numa_binding": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, P, method)),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the kernel, "
