@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
@@ -63,8 +64,9 @@ struct Knobs {
     int prefix_run = 8;          // SGM_PREFIX_RUN
     bool prefix_unbalanced = false;
     int prefix_ppl = 0;          // SGM_PREFIX_PPL: 0 = automatic, 1 | 2 forced
-    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, no_key2 = false, wide_bulk = false;
+    bool no_sort = false, no_wide = false, no_idx8 = false, no_h1 = false, no_h2 = false, no_small = false, wide_bulk = false;
     int dev_flags = 0;           // SGM_DEV_FLAGS: PlanDev::dev_flags
+    int key_mode = 0;            // SGM_KEY_MODE: 1 = one key bit per direction first (round-1 key)
     bool no_jit = false;         // SGM_NO_JIT: never build the plan-specialised small-plan kernel
     bool jit_sync = false;       // SGM_JIT_SYNC: build it inside the triggering call (default: background thread)
     long long jit_min_points = 4000000;  // SGM_JIT_MIN_POINTS: points seen by a plan before it is built
@@ -84,9 +86,9 @@ struct Knobs {
         k.no_idx8 = std::getenv("SGM_NO_IDX8") != nullptr;
         k.no_h1 = std::getenv("SGM_NO_H1") != nullptr;
         k.no_h2 = std::getenv("SGM_NO_H2") != nullptr;
-        k.no_key2 = std::getenv("SGM_NO_KEY2") != nullptr;
         k.wide_bulk = std::getenv("SGM_WIDE_BULK") != nullptr;
         if (const char* v = std::getenv("SGM_DEV_FLAGS")) k.dev_flags = std::atoi(v);
+        if (const char* v = std::getenv("SGM_KEY_MODE")) k.key_mode = std::atoi(v);
         k.no_small = std::getenv("SGM_NO_SMALL") != nullptr;
         k.no_jit = std::getenv("SGM_NO_JIT") != nullptr;
         k.jit_sync = std::getenv("SGM_JIT_SYNC") != nullptr;
@@ -1307,58 +1309,65 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     d.kind = kind; d.N = N; d.E = (int)entries.size(); d.B = B; d.T = (int)T;
     d.n_knots = (int)n_knots;
 
-    {   // locality key: the (up to 16) most used directions, threshold = middle knot of the
-        // smallest knot family with an interior knot used in that direction
+    {   // locality key (<= 16 bits): which bracket bits of which directions decide the most rows.
+        // A use of an entry with n knots depends on the leading ceil(log2(n + 1)) - 1 bits of the
+        // bracket search in its direction; benefit(d, b) = uses of direction d that depend on bit
+        // b.  The 16 most beneficial (direction, bit) pairs form the key (benefit is monotone in
+        // b, so a direction always gets a prefix of its bits); config 2 / 5: one bit for each of
+        // the 16 most used directions, config 3 (anisotropic): several bits for the leading
+        // directions, config 4 (d = 8): two bits per direction.
+        // SGM_KEY_MODE=1 (dev knob): one bit per direction first, spare bits as second level.
         std::vector<int64_t> usage(N, 0);
-        std::vector<int> small_fam(N, -1), second_fam(N, -1);
+        std::vector<int> fine_fam(N, -1);
+        std::vector<std::array<int64_t, 9>> dep(N);
+        for (auto& a : dep) a.fill(0);
+        auto bits_of = [](int n) { int b = 0; while ((1 << (b + 1)) < n + 1) ++b; return b; };   // ceil(log2(n+1)) - 1
         for (const TermDim& td : tdim) {
             const Entry& e = entries[td.ent];
             ++usage[e.dim];
-            if (e.n >= 3 && (small_fam[e.dim] < 0 || e.n < entries[small_fam[e.dim]].n))
-                small_fam[e.dim] = td.ent;
-            if (e.n >= 5 && (second_fam[e.dim] < 0 || e.n < entries[second_fam[e.dim]].n))
-                second_fam[e.dim] = td.ent;
+            if (e.n >= 3 && (fine_fam[e.dim] < 0 || e.n > entries[fine_fam[e.dim]].n)) fine_fam[e.dim] = td.ent;
+            const int nb = std::min(bits_of(e.n), 8);
+            for (int b = 0; b < nb; ++b) ++dep[e.dim][b];
         }
-        std::vector<int> order;
-        for (int n = 0; n < N; ++n) if (small_fam[n] >= 0) order.push_back(n);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return usage[a] > usage[b]; });
-        d.n_key = (int)std::min<size_t>(order.size(), 16);
-        // bit order (locality_key: entry 0 = most significant bit): most used direction first,
-        // so that neighbours in the sorted order differ in the least used directions; among
-        // equally used directions the LOWEST one goes last -- a differing bracket in a low
-        // direction is cheap for the prefix kernel, whose value tables are stored with the
-        // first active direction fastest (neighbouring brackets = neighbouring addresses)
-        order.resize((size_t)d.n_key);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return usage[a] != usage[b] ? usage[a] > usage[b] : a > b;
-        });
-        for (int i = 0; i < 16; ++i) d.key_dep[i] = -1;
-        for (int i = 0; i < d.n_key; ++i) {
-            const Entry& e = entries[small_fam[order[i]]];
-            d.key_dim[i] = e.dim;
-            d.key_thr[i] = desc->fam_knots[e.knot_off + e.n / 2];
-        }
-        // spare key bits (plans with fewer than 16 keyed directions, e.g. config 4 with d = 8):
-        // a second level per direction, most used first -- the quarter knots of the smallest
-        // family with at least 5 knots, chosen by the direction's first-level bit.  Points of one
-        // bin then share their brackets / patches two levels deep.
-        const int first_level = d.n_key;
-        plan->first_level_keys = first_level;
-        if (!plan->knobs.no_key2) {
-            std::vector<int> second;
-            for (int i = 0; i < first_level && first_level + (int)second.size() < 16; ++i)
-                if (second_fam[order[i]] >= 0) second.push_back(i);
-            const int total = first_level + (int)second.size();
-            for (size_t j = 0; j < second.size(); ++j) {
-                const int i = second[j], slot = first_level + (int)j;
-                const Entry& e = entries[second_fam[order[i]]];
-                d.key_dim[slot] = e.dim;
-                d.key_thr[slot] = desc->fam_knots[e.knot_off + e.n / 4];
-                d.key_thr2[slot] = desc->fam_knots[e.knot_off + (3 * e.n) / 4];
-                d.key_dep[slot] = (signed char)(total - 1 - i);       // bit position of entry i
+        struct Cand { int64_t benefit; int dim; int bit; };
+        std::vector<Cand> cands;
+        for (int n = 0; n < N; ++n) {
+            if (fine_fam[n] < 0) continue;
+            const int maxb = std::min(bits_of(entries[fine_fam[n]].n), 8);
+            for (int b = 0; b < maxb; ++b) {
+                int64_t ben = dep[n][b];
+                if (plan->knobs.key_mode == 1) ben = b == 0 ? ((int64_t)1 << 40) + usage[n] : (b == 1 ? usage[n] : 0);
+                if (ben > 0) cands.push_back(Cand{ben, n, b});
             }
-            d.n_key = total;
         }
+        // most beneficial first; ties: lower bit first, then the HIGHER direction (a differing
+        // bracket in a low direction is cheap for the kernels whose value tables are stored with
+        // the first active direction fastest: neighbouring brackets = neighbouring addresses)
+        std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+            if (a.benefit != b.benefit) return a.benefit > b.benefit;
+            if (a.bit != b.bit) return a.bit < b.bit;
+            return a.dim > b.dim;
+        });
+        if (cands.size() > 16) cands.resize(16);
+        std::vector<int> nbits(N, 0), first_pos(N, -1);
+        for (size_t i = 0; i < cands.size(); ++i) {
+            ++nbits[cands[i].dim];
+            if (first_pos[cands[i].dim] < 0) first_pos[cands[i].dim] = (int)i;
+        }
+        std::vector<int> gdims;
+        for (int n = 0; n < N; ++n) if (nbits[n] > 0) gdims.push_back(n);
+        std::sort(gdims.begin(), gdims.end(), [&](int a, int b) { return first_pos[a] < first_pos[b]; });
+        d.n_kgrp = (int)gdims.size();
+        d.n_key = 0;
+        for (int i = 0; i < d.n_kgrp; ++i) {
+            const Entry& e = entries[fine_fam[gdims[i]]];
+            d.kg_dim[i] = e.dim;
+            d.kg_off[i] = e.knot_off;
+            d.kg_n[i] = (unsigned short)e.n;
+            d.kg_bits[i] = (unsigned char)nbits[gdims[i]];
+            d.n_key += nbits[gdims[i]];
+        }
+        plan->first_level_keys = d.n_kgrp;
     }
     std::vector<double> coeff(desc->coeffs, desc->coeffs + T);
     std::vector<int> maps(desc->maps, desc->maps + desc->map_off[T]);

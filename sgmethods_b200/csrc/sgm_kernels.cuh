@@ -85,17 +85,17 @@ struct PlanDev {
     // the distance in doubles between the outputs of consecutive segments; null otherwise
     const int* seg_id;
     int64_t seg_stride;
-    // locality key of a point: bit i = x[key_dim[i]] >= key_thr[i] (middle knot of the
-    // coarsest knot family used in that direction), for the n_key most used directions
-    // Plans with fewer than 16 keyed directions spend the spare bits on a SECOND level: entry i
-    // with key_dep[i] >= 0 tests the quarter knot of the half selected by the (more significant)
-    // key bit key_dep[i]: x >= (that bit ? key_thr2[i] : key_thr[i]).
+    // locality key of a point (<= 16 bits): group i contributes kg_bits[i] bits, the leading bits
+    // of a binary search of x[kg_dim[i]] in the finest knot family used in that direction (kg_n
+    // knots at knots + kg_off): the coarse end of the bracket index on every level.  Groups are
+    // listed most significant first.
     int dev_flags;                     // development switches: 1 = strided entry fill, 2 = read all 7 member slots
-    int n_key;
-    int key_dim[16];
-    double key_thr[16];
-    double key_thr2[16];
-    signed char key_dep[16];
+    int n_key;                         // total key bits
+    int n_kgrp;
+    int kg_dim[16];
+    int kg_off[16];
+    unsigned short kg_n[16];
+    unsigned char kg_bits[16];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -1356,12 +1356,16 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned locality_key(const PlanDev& pl, const double* xp) {
     unsigned key = 0;
-    // the most used direction is the most significant bit: neighbours in the sorted order then
-    // differ in the least used directions first (matters when the bins are sparsely filled)
-    for (int i = 0; i < pl.n_key; ++i) {
-        const int dep = pl.key_dep[i];
-        const double thr = (dep >= 0 && ((key >> dep) & 1u)) ? pl.key_thr2[i] : pl.key_thr[i];
-        key |= (xp[pl.key_dim[i]] >= thr ? 1u : 0u) << (pl.n_key - 1 - i);
+    for (int i = 0; i < pl.n_kgrp; ++i) {
+        const double xv = xp[pl.kg_dim[i]];
+        const double* g = pl.knots + pl.kg_off[i];
+        int lo = 0, hi = pl.kg_n[i];
+        for (int b = 0; b < pl.kg_bits[i]; ++b) {
+            const int mid = (lo + hi) >> 1;
+            const bool up = xv >= __ldg(g + min(mid, (int)pl.kg_n[i] - 1));
+            key = (key << 1) | (up ? 1u : 0u);
+            if (up) lo = mid + 1; else hi = mid;
+        }
     }
     return key;
 }
