@@ -86,15 +86,26 @@ _BATCH_BYTES = 1 << 30
 def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
                              f, SG, u_on_SG, yy_rnd, L2_err_param, u_interp,
                              TP_inteporlant=TPPwLinearInterpolator, n_parallel=1,
-                             method="surplus"):
+                             method="surplus", extensions=None):
     """Args as in the reference: old reduced margin and its indicators (recycled where the
     index is still in the reduced margin), the current MidSet, knots / lev2knots, the
     function ``f``, the current sparse grid ``SG`` with the values ``u_on_SG``, random
     parameters ``yy_rnd``, the norm callback ``L2_err_param(u_ext, u)`` and the current
     interpolant's values ``u_interp`` on ``yy_rnd``.  Returns one indicator per row of
-    ``mid_set.reduced_margin``."""
+    ``mid_set.reduced_margin``.
+
+    ``extensions`` (not in the reference; ``method="surplus"`` only): pass a dict to receive, for
+    every candidate whose indicator was computed (key = its row in the reduced margin), what
+    the adaptive loop needs to move on WITHOUT re-evaluating or re-sampling anything once that
+    candidate is chosen -- the incremental update of the loop:
+    ``values`` = I_{Lambda + nu}[u](yy_rnd) = ``u_interp`` + surplus (the next iteration's
+    ``u_interp``), ``nodes`` / ``samples`` = the sparse-grid nodes that are new with nu and the
+    samples of ``f`` taken there (to be appended to ``SG`` / ``u_on_SG`` as ``old_xx`` /
+    ``old_samples`` of the next ``sample_on_SG``, which then calls ``f`` nowhere)."""
     assert old_RM.shape[0] == old_estimators.size
     assert method in ("surplus", "rebuild")
+    if extensions is not None and method != "surplus":
+        raise ValueError("extensions are produced by method='surplus'")
     reduced_margin = mid_set.reduced_margin
     card_rm = reduced_margin.shape[0]
     indicators = np.zeros(card_rm)
@@ -146,7 +157,7 @@ def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
         SG_cur = np.hstack((SG_cur, np.zeros((SG_cur.shape[0], N - SG_cur.shape[1]))))
     u_cur = np.asarray(u_interp, dtype=np.float64)
     u_cur_dev = torch.from_numpy(np.ascontiguousarray(u_cur.reshape(P, -1))).to(device)
-    on_gpu = isinstance(L2_err_param, MeanSquareNorm)
+    on_gpu = isinstance(L2_err_param, MeanSquareNorm) and extensions is None
     per_batch = max(1, int(_BATCH_BYTES // max(1, P * NF * 8)))
     for lo in range(0, len(to_compute), per_batch):
         batch = to_compute[lo:lo + per_batch]
@@ -185,6 +196,13 @@ def compute_GG_indicators_RM(old_RM, old_estimators, mid_set, knots, lev2knots,
             u_ext = (u_cur_dev.unsqueeze(0) + deltas).cpu().numpy()  # one D2H for the batch
             for j, i in enumerate(batch):
                 indicators[i] = L2_err_param(u_ext[j].reshape(u_cur.shape), u_interp)
+            if extensions is not None:
+                # nodes of candidate j = rows addressed by the maps of its terms; new = not in SG
+                for j, i in enumerate(batch):
+                    rows = np.unique(maps[map_off[seg_off[j]]:map_off[seg_off[j + 1]]])
+                    new = rows[~have[rows]]
+                    extensions[i] = {"values": u_ext[j].reshape(u_cur.shape), "nodes": nodes[new],
+                                     "samples": vals[new]}
         if kind == _lib.KIND_QUADRATIC and plan.take_flags() & _lib.FLAG_QUADRATIC_RIGHT:
             raise IndexError("pw-quadratic interpolation: a point lies right of the last knot")
         plan.close()

@@ -529,6 +529,51 @@ def test_error_indicators_against_reference_driver_outputs(name, method):
         assert len(calls) <= int(g[f"n_f_calls_{step}"])     # never more samples than the reference
 
 
+def test_adaptive_loop_moves_on_without_reevaluating_or_resampling():
+    """The incremental update of the adaptive loop: the indicator launch
+    hands back, for every candidate, the extended interpolant's values at the random points and
+    the samples taken on its new nodes; after choosing a candidate the next iteration needs no
+    evaluation and no call of f.  Checked against the reference's sequence (new SGInterpolant,
+    sample_on_SG with recycling, interpolate) over three adaptive steps."""
+    from sgmethods_b200.compute_error_indicators import compute_GG_indicators_RM
+    from sgmethods_b200.mid_set import MidSet
+    knots, lev = nodes_1d.unbounded_nodes_nested, (lambda n: 2 ** (n + 1) - 1)
+    calls = []
+
+    def f(y):
+        calls.append(1)
+        return np.array([np.exp(-0.3 * np.sum(y * y)), np.sin(np.sum(y))])
+    norm = lambda a, b: float(np.sqrt(np.mean(np.sum((a - b) ** 2, axis=1))))  # noqa: E731
+    ms = MidSet(track_reduced_margin=True)
+    for op, arg in (("e", 0), ("d", None), ("e", 1), ("d", None), ("e", 0), ("e", 2)):
+        ms.enlarge_from_margin(arg) if op == "e" else ms.increase_dim()
+    yy = np.random.default_rng(21).normal(size=(3000, 6))
+    cur = SGInterpolant(ms.mid_set, knots, lev, verbose=False)
+    SG, u_on_SG = cur.SG, cur.sample_on_SG(f)
+    u_interp = cur.interpolate(yy, u_on_SG)
+    none_rm, none_est = np.zeros((0, 0), dtype=int), np.zeros(0)   # no recycled indicators: all computed
+    for step in range(3):
+        ext = {}
+        est = compute_GG_indicators_RM(none_rm, none_est, ms, knots, lev, f, SG, u_on_SG, yy, norm,
+                                       u_interp, extensions=ext)
+        assert sorted(ext) == list(range(ms.get_cardinality_reduced_margin()))
+        best = int(np.argmax(est))
+        nu = ms.reduced_margin[best]
+        ms.enlarge_from_margin(int(np.flatnonzero((ms.margin == nu).all(axis=1))[0]))
+        # reference sequence for the next iteration, fed with what the launch handed back
+        N = ms.get_dim()
+        pad = lambda a: np.hstack((a, np.zeros((a.shape[0], N - a.shape[1]))))  # noqa: E731
+        old_xx = np.vstack((pad(SG), pad(ext[best]["nodes"])))
+        old_samples = np.vstack((u_on_SG, ext[best]["samples"]))
+        nxt = SGInterpolant(ms.mid_set, knots, lev, verbose=False)
+        n_before = len(calls)
+        u_next = nxt.sample_on_SG(f, old_xx=old_xx, old_samples=old_samples)
+        assert len(calls) == n_before                     # every node recycled: f is not called
+        full = nxt.interpolate(yy, u_next)                # what the loop no longer has to compute
+        assert rel_err(ext[best]["values"], full) <= 1e-12
+        SG, u_on_SG, u_interp = nxt.SG, u_next, ext[best]["values"]
+
+
 def test_pipelined_host_path_equals_device_path():
     """Pinned host points take the chunked copy/compute pipeline; same bits as one launch."""
     import torch
