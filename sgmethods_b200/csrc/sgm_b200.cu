@@ -357,6 +357,10 @@ bool use_prefix_kernel(const sgm_plan* plan, int64_t P) {
     if (!plan->prefix_ok || plan->dev.kind != SGM_PW_LINEAR) return false;
     if (plan->knobs.force_kernel) return plan->knobs.force_kernel == 3 && plan->prefix_launch_ok;
     if (plan->dev.T < 32 && P >= 16384) return false;         // few terms, many points: kernel A
+    // at most one tile per SM: the time is ONE tile's latency over all terms, and the split kernel
+    // puts 16-32 warps on a tile where the prefix kernel has 8 (validation sample of
+    // method="auto", 256 points of config 2: 0.24 ms against 0.56 ms)
+    if ((P + 31) / 32 <= plan->sm_count) return false;
     return plan->prefix_wins > 0;                             // decided at plan creation
 }
 

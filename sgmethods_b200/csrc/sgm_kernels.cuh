@@ -89,7 +89,7 @@ struct PlanDev {
     // of a binary search of x[kg_dim[i]] in the finest knot family used in that direction (kg_n
     // knots at knots + kg_off): the coarse end of the bracket index on every level.  Groups are
     // listed most significant first.
-    int dev_flags;                     // development switches: 1 = strided entry fill, 2 = read all 7 member slots
+    int dev_flags;                     // development switches: 1 = strided entry fill, 2 = read all 7 member slots, 4 = no record prefetch
     int n_key;                         // total key bits
     int n_kgrp;
     int kg_dim[16];
@@ -702,13 +702,30 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
         for (int t0 = 0; t0 < pl.T; t0 += chunk, ++gc) {
             double* sp = sP + (size_t)(gc & 1u) * chunk * 32 + lane;
             const int nt = min(chunk, pl.T - t0);
+            // the record of a warp's NEXT term is requested before the current term is walked:
+            // with few resident tiles (validation samples, small batches) a term is otherwise a
+            // chain of two dependent L2 round trips (record, then gathers)
+            int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+            if (warp < nt) {
+                n0 = __ldg(rec4 + 2 * (t0 + warp));
+                if (KIND == SGM_PW_LINEAR) n1 = __ldg(rec4 + 2 * (t0 + warp) + 1);
+            }
             for (int tl = warp; tl < nt; tl += W) {
                 const int t = t0 + tl;
-                const int4 r0 = __ldg(rec4 + 2 * t);            // coeff (x,y), val_off, info
+                if (pl.dev_flags & 4) {                          // dev switch: no prefetch
+                    n0 = __ldg(rec4 + 2 * t);
+                    if (KIND == SGM_PW_LINEAR) n1 = __ldg(rec4 + 2 * t + 1);
+                }
+                const int4 r0 = n0;                              // coeff (x,y), val_off, info
+                const int4 r1p = n1;
+                if (!(pl.dev_flags & 4) && tl + W < nt) {
+                    n0 = __ldg(rec4 + 2 * (t + W));
+                    if (KIND == SGM_PW_LINEAR) n1 = __ldg(rec4 + 2 * (t + W) + 1);
+                }
                 const double coef = __hiloint2double(r0.y, r0.x);
                 double tp;
                 if (KIND == SGM_PW_LINEAR && (r0.w & TERMREC_PACKED)) {
-                    const int4 r1 = __ldg(rec4 + 2 * t + 1);
+                    const int4 r1 = r1p;
                     switch (r0.w & 0xff) {
                         case 0: tp = G[r0.z]; break;
                         case 1: tp = linear_term_packed<1, IdxT>(r1, bas, idx, G + r0.z); break;
