@@ -263,11 +263,19 @@ int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, 
 /* All batches of the hierarchisation in one call: batch b covers entries
  * [batch_off[b], batch_off[b+1]) of the concatenated child / pa / pb / wa / wb arrays (device);
  * batch_off is given both on the host and on the device (n_batches + 1 entries).  Small
- * tables run as ONE launch of one block, large ones as one launch per batch. */
+ * tables run as ONE launch of one thread-block cluster, large ones as one launch per batch. */
 int sgm_hier_apply_batches(double* alpha, int64_t NF, int64_t ld, const int32_t* child,
                            const int32_t* pa, const int32_t* pb, const double* wa, const double* wb,
                            const int64_t* batch_off_host, const int64_t* batch_off_dev,
                            int32_t n_batches, void* stream);
+
+/* Validation of a work-reduced evaluation against the exact one (method="auto",
+ * sparse_grid_interpolant.py of this repository; no reference counterpart): writes
+ *   out[0] = max_i |a_i - b_i| / max(max_i |b_i|, tiny)      over the n entries,
+ * where an entry that is NaN in BOTH arrays counts as agreement (the reference's Lagrange
+ * operator returns NaN on a knot) and an entry that is NaN in one of them makes the result NaN.
+ * max |b| = 0 divides by 1.  a, b, out: device, fp64; one small launch, no host sync. */
+int sgm_max_rel_deviation(const double* a, const double* b, int64_t n, double* out, void* stream);
 
 /* W[p, :] = Levy-Ciesielski expansion of Brownian motion on [0, T] at times tt for the
  * parameter vector yy[p, 0:d]  (reference: param_LC_Brownian_motion,

@@ -53,6 +53,7 @@ SIGNATURES = {
                                       c_vp]),
     "sgm_hier_apply_batches": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, p_i64,
                                               c_vp, c_i32, c_vp]),
+    "sgm_max_rel_deviation": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "sgm_grid_num_nodes": (c_i64, [c_vp]),
     "sgm_grid_map_size": (c_i64, [c_vp]),
     "sgm_grid_nnz": (c_i64, [c_vp]),

@@ -1685,6 +1685,13 @@ int sgm_hier_apply(double* alpha, int64_t NF, int64_t ld, const int32_t* child, 
     return SGM_OK;
 }
 
+int sgm_max_rel_deviation(const double* a, const double* b, int64_t n, double* out, void* stream) {
+    if (n < 0 || !out || (n > 0 && (!a || !b))) return sgm_fail(SGM_ERR_INVALID, "max_rel_deviation: bad argument");
+    sgm::max_rel_deviation_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out);
+    SGM_CUDA(cudaGetLastError());
+    return SGM_OK;
+}
+
 int sgm_hier_apply_batches(double* alpha, int64_t NF, int64_t ld, const int32_t* child,
                            const int32_t* pa, const int32_t* pb, const double* wa, const double* wb,
                            const int64_t* batch_off_host, const int64_t* batch_off_dev,

@@ -2268,6 +2268,45 @@ eval_cols_wide4_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P
                                           quads_per_block, perm, ncols);
 }
 
+// max |a - b| / max |b| with the NaN rule of sgm_max_rel_deviation (one block).
+__global__ void __launch_bounds__(1024)
+max_rel_deviation_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                         double* __restrict__ out) {
+    __shared__ double s_diff[32], s_abs[32];
+    __shared__ int s_bad[32];
+    double md = 0.0, ma = 0.0;
+    int bad = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = a[i], y = b[i];
+        const bool nx = x != x, ny = y != y;
+        if (nx && ny) continue;
+        if (nx || ny) { bad = 1; continue; }
+        md = fmax(md, fabs(x - y));
+        ma = fmax(ma, fabs(y));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, off));
+        ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_diff[warp] = md; s_abs[warp] = ma; s_bad[warp] = bad; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        md = lane < nw ? s_diff[lane] : 0.0;
+        ma = lane < nw ? s_abs[lane] : 0.0;
+        bad = lane < nw ? s_bad[lane] : 0;
+        for (int off = 16; off > 0; off >>= 1) {
+            md = fmax(md, __shfl_xor_sync(0xffffffffu, md, off));
+            ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+        }
+        if (lane == 0)
+            out[0] = bad ? __longlong_as_double(0x7ff8000000000000ll) : md / (ma > 0.0 ? ma : 1.0);
+    }
+}
+
 // One batch of the dimension-wise hierarchisation (surplus = value - coarser interpolant).
 __global__ void hier_apply_kernel(double* __restrict__ alpha, int64_t NF, int64_t ld,
                                   const int* __restrict__ child, const int* __restrict__ pa,
@@ -2298,10 +2337,36 @@ hier_apply_all_kernel(double* __restrict__ alpha, int64_t NF, int64_t ld,
                       int n_batches) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    // The index / weight records of a thread's FIRST element of the next batch do not depend on
+    // alpha: they are requested before the barrier, so that after it a batch costs one round trip
+    // (the alpha values) instead of two.
+    int c_ch = 0, c_pa = 0, c_pb = -1;
+    double c_wa = 0.0, c_wb = 0.0;
+    int64_t c_col = 0;
+    auto fetch = [&](int b) {
+        if (b >= n_batches) return;
+        const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
+        if (tid < n * NF) {
+            const int64_t it = lo + tid / NF;
+            c_col = tid % NF;
+            c_ch = child[it]; c_pa = pa[it]; c_pb = pb[it]; c_wa = wa[it]; c_wb = wb[it];
+        }
+    };
+    fetch(0);
     for (int b = 0; b < n_batches; ++b) {
         const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
         const int64_t total = n * NF;
-        for (int64_t i = tid; i < total; i += nthreads) {
+        const bool mine = tid < total;
+        const int ch0 = c_ch, pa0 = c_pa, pb0 = c_pb;
+        const double wa0 = c_wa, wb0 = c_wb;
+        const int64_t col0 = c_col;
+        fetch(b + 1);
+        if (mine) {
+            double coarse = wa0 * alpha[(int64_t)pa0 * ld + col0];
+            if (pb0 >= 0) coarse = coarse + wb0 * alpha[(int64_t)pb0 * ld + col0];
+            alpha[(int64_t)ch0 * ld + col0] -= coarse;
+        }
+        for (int64_t i = tid + nthreads; i < total; i += nthreads) {
             const int64_t it = lo + i / NF, c = i % NF;
             double coarse = wa[it] * alpha[(int64_t)pa[it] * ld + c];
             if (pb[it] >= 0) coarse = coarse + wb[it] * alpha[(int64_t)pb[it] * ld + c];

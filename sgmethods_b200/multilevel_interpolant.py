@@ -227,7 +227,8 @@ class MLInterpolant:
     def _evaluate(self, parts, blocks, yy, missing, method="combination"):
         """parts as in ``_fused_plan``; blocks: list of sample arrays (block id = position)."""
         from ._device import torch_cuda
-        from .sparse_grid_interpolant import AUTO_MIN_POINTS, AUTO_SAMPLE, AUTO_TOL, _to_device
+        from .sparse_grid_interpolant import (AUTO_MIN_POINTS, AUTO_SAMPLE, AUTO_TOL, _max_rel_deviation,
+                                              _to_device)
         torch = torch_cuda()
         as_torch = isinstance(yy, torch.Tensor)
         device = yy.device if as_torch and yy.is_cuda else \
@@ -260,10 +261,7 @@ class MLInterpolant:
             # validate THIS call: a sample of the batch through both forms, like SGInterpolant
             xs = x[::max(1, x.shape[0] // AUTO_SAMPLE)][:AUTO_SAMPLE].contiguous()
             exact, fast = plan.eval(xs, F), hier[0].eval(xs, hier[1])
-            both_nan = exact.isnan() & fast.isnan()
-            scale = torch.where(both_nan, torch.zeros_like(exact), exact.abs()).max()
-            dev = float(torch.where(both_nan, torch.zeros_like(exact), (fast - exact).abs()).max() /
-                        torch.where(scale > 0, scale, torch.ones_like(scale)))
+            dev = float(_max_rel_deviation(torch, fast, exact))
             ok = bool(np.isfinite(dev)) and dev <= AUTO_TOL
             self.auto_validation = {"enabled": ok, "max_rel_deviation": dev, "tolerance": AUTO_TOL,
                                     "sample_points": int(xs.shape[0])}
