@@ -252,7 +252,7 @@ def config4_level(k=3, d=8):
 
 
 @pytest.mark.parametrize("data", ["random", "smooth"])
-@pytest.mark.parametrize("NF", [1, 200])
+@pytest.mark.parametrize("NF", [1, 200, 300])      # 300: four points per warp on 256-column tiles + ragged tile
 def test_config4_shape_quadratic_hierarchical_within_contract(data, NF):
     """BASELINE config 4's finest level (pw-quadratic, d = 8, Smolyak level 3, Clenshaw-Curtis
     knots 1, 3, 5, 9): 333 basis tuples instead of 165 terms x 3^k nodes."""
@@ -418,3 +418,31 @@ def test_random_downward_closed_sets_hierarchical_kernels(kind, seed):
         exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(-1, NF)
         assert rel_dev(exact[:40], ref) <= TOL
         assert rel_dev(fast[:40], ref) <= TOL and rel_dev(fast, exact) <= TOL
+
+
+def test_hierarchical_column_kernel_flavours_agree_bit_for_bit(monkeypatch):
+    """One, two and four points per warp (128- and 256-column tiles) of the hierarchical column
+    kernels and the bulk-copy experiment kernel compute the same bits."""
+    import torch
+    it = config4_level(3, 6)
+    rng = np.random.default_rng(16)
+    hp = it.hierarchical()
+    plan = hp._dev(0)[0]
+    x = torch.from_numpy(rng.uniform(-1.1, 1.0, (5003, 6))).cuda()
+    f = torch.from_numpy(rng.normal(size=(it.num_nodes, 610))).cuda()      # 2 full tiles + ragged
+    alpha = hp.surpluses(f)
+    ref = None
+    for env in ({"SGM_WIDE_PTS": "2"}, {"SGM_WIDE_PTS": "4"}, {"SGM_WIDE_PTS": "8"}, {}, {"SGM_WIDE_BULK": "1"}):
+        for k in ("SGM_WIDE_PTS", "SGM_WIDE_BULK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plan.reload_knobs()
+        out = plan.eval(x, alpha)
+        ref = out if ref is None else ref
+        assert torch.equal(out, ref), env
+    for k in ("SGM_WIDE_PTS", "SGM_WIDE_BULK"):
+        monkeypatch.delenv(k, raising=False)
+    plan.reload_knobs()
+    exact = it.interpolate(x, f, method="combination")
+    assert rel_dev(ref.cpu().numpy(), exact.cpu().numpy()) <= TOL
