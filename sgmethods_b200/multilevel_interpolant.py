@@ -51,6 +51,7 @@ class MLInterpolant:
         self._restricted = {}
         self._plans = {}
         self._hier = None
+        self._hier_moves_dev = {}
         self.auto_validation = None
 
     # ----------------------------------------------------------------------------- sampling
@@ -214,7 +215,7 @@ class MLInterpolant:
         hps, moves = self._hierarchical()
         top = hps[-1]
         alpha = torch.empty((top.M, fs[0].shape[1]), dtype=torch.float64, device=device)
-        cache = self.__dict__.setdefault("_hier_moves_dev", {})
+        cache = self._hier_moves_dev
         for k, (hp, f) in enumerate(zip(hps, fs)):
             key = (device.index, k)
             if key not in cache:

@@ -348,9 +348,12 @@ class SGInterpolant:
         # NaN where the reference is NaN (Lagrange on a knot) counts as agreement; NaN in one of
         # the two only makes the deviation NaN and fails the validation (sgm_max_rel_deviation)
         dev = _max_rel_deviation(torch, fast, exact)
-        host = getattr(self, "_auto_host", None)
+        # one pinned scalar per (device, stream): calls on different streams never share it
+        hosts = self.__dict__.setdefault("_auto_hosts", {})
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        host = hosts.get(key)
         if host is None:
-            host = self._auto_host = torch.empty(1, dtype=torch.float64).pin_memory()
+            host = hosts[key] = torch.empty(1, dtype=torch.float64).pin_memory()
         host.copy_(dev.reshape(1), non_blocking=True)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(device))
