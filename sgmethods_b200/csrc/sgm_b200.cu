@@ -225,8 +225,11 @@ bool use_h2_kernel(const sgm_plan* plan) {
 }
 constexpr int64_t kSortMinPoints = 32768;       // scalar kernels
 constexpr int64_t kSortMinPointsCols = 4096;    // wide column kernel with two points per warp
-size_t sort_scratch_bytes(int64_t P) {
-    return align_up((size_t)P * 4, 256) + 65536 * 4 + 64 * 4 + align_up((size_t)P * 2, 256);
+size_t sort_scratch_bytes(int64_t P) {      // perm | bins | block totals | keys | tile counter
+    return align_up((size_t)P * 4, 256) + 65536 * 4 + 64 * 4 + align_up((size_t)P * 2, 256) + 256;
+}
+int* sort_tile_counter(unsigned char* scratch, int64_t P) {
+    return reinterpret_cast<int*>(scratch + sort_scratch_bytes(P) - 256);
 }
 
 // Launch shape of kernel A2 (32 points x W warps per block, terms split over the warps).
@@ -307,7 +310,7 @@ int locality_sort(sgm_plan* plan, const double* x, int64_t P, int64_t ldx, unsig
     const int scan_blocks = (nbins + 1023) / 1024;
     SGM_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * 4, stream));
     const int sblocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)plan->sm_count * 8);
-    sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys);
+    sgm::sort_hist_kernel<<<sblocks, 256, 0, stream>>>(plan->dev, x, P, ldx, hist, keys, sort_tile_counter(scratch, P));
     sgm::sort_scan_kernel<<<scan_blocks, 1024, 0, stream>>>(hist, nbins, block_total);
     sgm::sort_scatter_kernel<<<sblocks, 256, 0, stream>>>(keys, P, hist, block_total, scan_blocks, perm_w);
     SGM_CUDA(cudaGetLastError());
@@ -537,7 +540,14 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sh.kern, sh.warps * 32, smem);
             if (bps < 1) continue;
             blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * bps);
-            sh.kern<<<(unsigned)blocks, sh.warps * 32, smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+            // sorted batches: tiles are handed out from a global counter (last word of the sort
+            // scratch, zeroed by the sort's first kernel), so that the blocks of an
+            // SM that was busy when the kernel started take fewer tiles (dev knob SGM_DEV_FLAGS
+            // bit 3 = static striding)
+            PlanDev pd = plan->dev;
+            pd.tile_counter = nullptr;
+            if (perm && !(plan->knobs.dev_flags & 8)) pd.tile_counter = sort_tile_counter(scratch, P);   // zeroed by the sort
+            sh.kern<<<(unsigned)blocks, sh.warps * 32, smem, stream>>>(pd, x, P, ldx, G, out, ldo,
                                                                      scale, accumulate, perm);
             SGM_CUDA(cudaGetLastError());
             return SGM_OK;

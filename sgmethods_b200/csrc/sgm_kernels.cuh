@@ -89,6 +89,7 @@ struct PlanDev {
     // of a binary search of x[kg_dim[i]] in the finest knot family used in that direction (kg_n
     // knots at knots + kg_off): the coarse end of the bracket index on every level.  Groups are
     // listed most significant first.
+    int* tile_counter;                 // grouped kernel: global tile counter for dynamic tile scheduling (null: static)
     int dev_flags;                     // development switches: 1 = strided entry fill, 2 = read all 7 member slots, 4 = no record prefetch
     int n_key;                         // total key bits
     int n_kgrp;
@@ -1263,8 +1264,28 @@ eval_hier_groups_kernel(const PlanDev pl, const double* __restrict__ x, int64_t 
     const int64_t tile_begin = CONTIG ? n_tiles * blockIdx.x / gridDim.x : blockIdx.x;
     const int64_t tile_end = CONTIG ? n_tiles * (blockIdx.x + 1) / gridDim.x : n_tiles;
     const int64_t tile_step = CONTIG ? 1 : gridDim.x;
-    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int64_t slot_p = (tile << 5) + lane;
+    // dynamic tiles (pl.tile_counter): a block takes its next tile from a global counter, so that
+    // blocks which start late -- their SM was busy with another stream's small kernels, e.g. the
+    // validation sample of method="auto" -- simply process fewer tiles
+    const bool dyn = !CONTIG && pl.tile_counter != nullptr;
+    int64_t tile = tile_begin;
+    int next_dyn = 0;                    // thread 0: the tile after this one, requested a tile ahead
+    if (dyn && threadIdx.x == 0) next_dyn = atomicAdd(pl.tile_counter, 1);
+    for (;;) {
+        if (dyn) {
+            if (threadIdx.x == 0) {
+                sCounter[1] = next_dyn;
+                if (next_dyn < n_tiles) next_dyn = atomicAdd(pl.tile_counter, 1);   // used one tile later
+            }
+            __syncthreads();
+            tile = sCounter[1];
+            if (tile >= n_tiles) break;
+        } else if (tile >= tile_end) {
+            break;
+        }
+        const int64_t this_tile = tile;
+        if (!dyn) tile += tile_step;
+        const int64_t slot_p = (this_tile << 5) + lane;
         const bool valid = slot_p < P;
         const int64_t p = perm ? (int64_t)perm[valid ? slot_p : P - 1] : (valid ? slot_p : P - 1);
         const double* xp = x + p * ldx;
@@ -1388,7 +1409,8 @@ __device__ __forceinline__ unsigned locality_key(const PlanDev& pl, const double
 }
 __global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x, int64_t P,
                                  int64_t ldx, unsigned* __restrict__ hist,
-                                 unsigned short* __restrict__ keys) {
+                                 unsigned short* __restrict__ keys, int* __restrict__ tile_counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;   // for the kernel that follows the sort
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
          p += (int64_t)gridDim.x * blockDim.x) {
         const unsigned key = locality_key(pl, x + p * ldx);

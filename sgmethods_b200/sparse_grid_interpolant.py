@@ -336,27 +336,43 @@ class SGInterpolant:
         a sample of the batch (up to AUTO_SAMPLE rows spread over it) with the caller's nodal
         values; max|hier - exact| / max|exact| goes to a pinned host scalar.  Returns
         (pinned scalar, event recorded after its copy)."""
+        # The sample runs on a SIDE stream, enqueued before the batch: its few blocks take some SMs
+        # for a fraction of a millisecond while the batch kernel (dynamic tile scheduling) already
+        # runs on the others, instead of the batch waiting for two latency-bound small launches.
+        main = torch.cuda.current_stream(device)
+        sides = self.__dict__.setdefault("_auto_streams", {})
+        side = sides.get(device.index)
+        if side is None:
+            side = sides[device.index] = torch.cuda.Stream(device)
+        if not AUTO_SIDE_STREAM:
+            side = main
+        ready = torch.cuda.Event()
+        ready.record(main)                   # nodal values, surpluses and points are ready here
+        side.wait_event(ready)
         step = max(1, host_rows // AUTO_SAMPLE)
-        xs = x_new[::step][:AUTO_SAMPLE]
-        if isinstance(xs, np.ndarray):
-            xs = np.ascontiguousarray(xs[:, :self.N])
-        xs = _to_device(torch, xs, device)
-        if xs.shape[1] > self.N:
-            xs = xs[:, :self.N].contiguous()
-        exact = self.device_plan(device.index).eval(xs, f)
-        fast = hp._dev(device.index)[0].eval(xs, alpha)
-        # NaN where the reference is NaN (Lagrange on a knot) counts as agreement; NaN in one of
-        # the two only makes the deviation NaN and fails the validation (sgm_max_rel_deviation)
-        dev = _max_rel_deviation(torch, fast, exact)
-        # one pinned scalar per (device, stream): calls on different streams never share it
-        hosts = self.__dict__.setdefault("_auto_hosts", {})
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-        host = hosts.get(key)
-        if host is None:
-            host = hosts[key] = torch.empty(1, dtype=torch.float64).pin_memory()
-        host.copy_(dev.reshape(1), non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            xs = x_new[::step][:AUTO_SAMPLE]
+            if isinstance(xs, np.ndarray):
+                xs = np.ascontiguousarray(xs[:, :self.N])
+            xs = _to_device(torch, xs, device)
+            if xs.shape[1] > self.N:
+                xs = xs[:, :self.N].contiguous()
+            fast = hp._dev(device.index)[0].eval(xs, alpha)
+            exact = self.device_plan(device.index).eval(xs, f)
+            # NaN where the reference is NaN (Lagrange on a knot) counts as agreement; NaN in one
+            # of the two makes the deviation NaN and fails the validation (sgm_max_rel_deviation)
+            dev = _max_rel_deviation(torch, fast, exact)
+            # one pinned scalar per device: the side stream serialises the calls that use it
+            hosts = self.__dict__.setdefault("_auto_hosts", {})
+            host = hosts.get(device.index)
+            if host is None:
+                host = hosts[device.index] = torch.empty(1, dtype=torch.float64).pin_memory()
+            host.copy_(dev.reshape(1), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+            # tensors of this block belong to the side stream's allocator pool; the inputs
+            # (x_new, f, alpha) outlive the sample because the verdict is always read (a host
+            # synchronisation on `done`) before interpolate() returns
         return host, done, int(xs.shape[0])
 
     def _auto_verdict(self, host, done, n_sample):
@@ -468,6 +484,7 @@ DEFAULT_METHOD = "auto"
 AUTO_MIN_POINTS = 8192      # smaller batches stay on the exact kernels
 AUTO_SAMPLE = 256           # rows of the first large batch evaluated by both kernels
 AUTO_TOL = 2.5e-13          # max |hier - exact| / max |exact| that enables the form
+AUTO_SIDE_STREAM = True     # the validation sample runs on a side stream, next to the batch kernel
 
 
 # rows per host->device chunk of the pipelined path: a whole number of waves of the scalar

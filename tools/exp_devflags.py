@@ -28,7 +28,7 @@ for name, P in (("c2", 10 ** 6), ("c5", 10 ** 6)):
     hplan, eplan = hp._dev(0)[0], it.device_plan(0)
     alpha = hp.surpluses(f)
     for rnd in range(2):
-        for flags in (0, 1, 2, 3):
+        for flags in (0, 8, 0, 8):
             os.environ["SGM_DEV_FLAGS"] = str(flags)
             hplan.reload_knobs(); eplan.reload_knobs()
             th = timed(lambda: hplan.eval(x, alpha))
