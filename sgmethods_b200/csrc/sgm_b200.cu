@@ -490,7 +490,9 @@ int launch_points_prefix(sgm_plan* plan, const double* x, int64_t P, int64_t ldx
     const int* perm = nullptr;
     int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
     if (rc) return rc;
-    L.kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+    PlanDev pd = plan->dev;                                   // sorted batches: dynamic tiles
+    pd.tile_counter = (perm && !(plan->knobs.dev_flags & 8)) ? sort_tile_counter(scratch, P) : nullptr;
+    L.kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(pd, x, P, ldx, G, out, ldo,
                                                               scale, accumulate, perm);
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;
@@ -574,7 +576,9 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
     }
     SplitKernel kern = split_kernel_for<KIND>(L.warps, L.chunk, L.idx8);
     SGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(plan->dev, x, P, ldx, G, out, ldo,
+    PlanDev pd = plan->dev;                                   // sorted batches: dynamic tiles
+    pd.tile_counter = (perm && !(plan->knobs.dev_flags & 8)) ? sort_tile_counter(scratch, P) : nullptr;
+    kern<<<(unsigned)blocks, L.warps * 32, L.smem, stream>>>(pd, x, P, ldx, G, out, ldo,
                                                             scale, accumulate, perm);
     SGM_CUDA(cudaGetLastError());
     return SGM_OK;

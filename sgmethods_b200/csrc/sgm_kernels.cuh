@@ -672,7 +672,22 @@ eval_points_split_kernel(const PlanDev pl, const double* __restrict__ x, int64_t
 
     const int64_t n_tiles = (P + 31) >> 5;
     unsigned gc = 0;                                           // chunk counter (block-uniform)
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // dynamic tiles (pl.tile_counter, sorted batches): the next tile comes from a global counter,
+    // requested one tile ahead by thread 0
+    __shared__ int s_dyn_tile;
+    const bool dyn_tiles = pl.tile_counter != nullptr;
+    int next_dyn = 0;
+    if (dyn_tiles && threadIdx.x == 0) next_dyn = atomicAdd(pl.tile_counter, 1);
+    for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
+        if (dyn_tiles) {
+            if (threadIdx.x == 0) {
+                s_dyn_tile = next_dyn;
+                if (next_dyn < n_tiles) next_dyn = atomicAdd(pl.tile_counter, 1);
+            }
+            __syncthreads();
+            tile = s_dyn_tile;
+        }
+        if (tile >= n_tiles) break;
         // lanes of a tile = 32 consecutive points, or 32 consecutive entries of the locality
         // permutation (points whose coarse brackets agree gather from the same cache lines)
         const int64_t slot = (tile << 5) + lane;
@@ -841,7 +856,22 @@ eval_points_prefix_kernel(const PlanDev pl, const double* __restrict__ x, int64_
 
     const int64_t n_tiles = (P + TPTS - 1) / TPTS;
     unsigned gc = 0;                                           // chunk counter (block-uniform)
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // dynamic tiles (pl.tile_counter, sorted batches): the next tile comes from a global counter,
+    // requested one tile ahead by thread 0
+    __shared__ int s_dyn_tile;
+    const bool dyn_tiles = pl.tile_counter != nullptr;
+    int next_dyn = 0;
+    if (dyn_tiles && threadIdx.x == 0) next_dyn = atomicAdd(pl.tile_counter, 1);
+    for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
+        if (dyn_tiles) {
+            if (threadIdx.x == 0) {
+                s_dyn_tile = next_dyn;
+                if (next_dyn < n_tiles) next_dyn = atomicAdd(pl.tile_counter, 1);
+            }
+            __syncthreads();
+            tile = s_dyn_tile;
+        }
+        if (tile >= n_tiles) break;
         bool valid[PPL];
         int64_t p[PPL];
 #pragma unroll
