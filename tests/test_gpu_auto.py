@@ -446,3 +446,27 @@ def test_hierarchical_column_kernel_flavours_agree_bit_for_bit(monkeypatch):
     plan.reload_knobs()
     exact = it.interpolate(x, f, method="combination")
     assert rel_dev(ref.cpu().numpy(), exact.cpu().numpy()) <= TOL
+
+
+def test_max_rel_deviation_kernel_nan_rules():
+    """sgm_max_rel_deviation (the validation's comparison): NaN in both arrays is agreement, NaN
+    in one makes the result NaN, max |b| = 0 divides by 1; sizes across the block reduction."""
+    import torch
+    rng = np.random.default_rng(17)
+    for n in (1, 31, 1024, 70001):
+        a = rng.normal(size=n)
+        b = a + 1e-9 * rng.normal(size=n)
+        want = np.max(np.abs(a - b)) / np.max(np.abs(b))
+        got = float(sgi._max_rel_deviation(torch, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+        assert abs(got - want) <= 1e-15 * max(1.0, want) + 1e-25
+        if n > 1:
+            a2, b2 = a.copy(), b.copy()
+            a2[n // 2] = b2[n // 2] = np.nan                      # NaN in both: ignored
+            got = float(sgi._max_rel_deviation(torch, torch.from_numpy(a2).cuda(), torch.from_numpy(b2).cuda()))
+            keep = np.arange(n) != n // 2
+            assert abs(got - np.max(np.abs(a - b)[keep]) / np.max(np.abs(b[keep]))) <= 1e-15
+            b2[n // 2] = 1.0                                      # NaN in one: NaN
+            assert np.isnan(float(sgi._max_rel_deviation(torch, torch.from_numpy(a2).cuda(),
+                                                         torch.from_numpy(b2).cuda())))
+    z = torch.zeros(5, dtype=torch.float64, device="cuda")
+    assert float(sgi._max_rel_deviation(torch, z + 0.25, z)) == 0.25
