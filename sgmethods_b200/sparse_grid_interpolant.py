@@ -270,8 +270,14 @@ class SGInterpolant:
             copier.wait_event(after)
         else:
             copier.wait_stream(compute)
-        for i, lo in enumerate(range(0, P, _H2D_CHUNK)):
-            hi = min(P, lo + _H2D_CHUNK)
+        # a short first chunk (nothing overlaps its transfer), then the steady size
+        bounds, lo = [], 0
+        first = min(_H2D_FIRST, _H2D_CHUNK)
+        while lo < P:
+            hi = min(P, lo + (first if not bounds else _H2D_CHUNK))
+            bounds.append((lo, hi))
+            lo = hi
+        for i, (lo, hi) in enumerate(bounds):
             b = i % 2
             if is_numpy:
                 buf = staging[b]
@@ -431,7 +437,7 @@ class SGInterpolant:
             x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
         big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
             x_new.dtype == np.float64 and x_new.shape[1] >= self.N
-        pipelined = (pinned or big_numpy) and host_rows >= 4 * _H2D_CHUNK
+        pipelined = (pinned or big_numpy) and host_rows >= _H2D_MIN_ROWS
         entry = None
         if pipelined:
             entry = torch.cuda.Event()
@@ -445,12 +451,17 @@ class SGInterpolant:
             if method == "auto":
                 pending = self._auto_validation_launch(torch, hp, x_new, f, f_eval, device, host_rows)
         if pipelined:
-            def choose(pending=pending, plan=plan, f_eval=f_eval):
-                if pending is not None and not self._auto_verdict(*pending):
-                    return exact_plan, f
-                return plan, f_eval
+            # optimistic: the chunks are enqueued with the fast plan while the validation sample
+            # runs on its side stream; a failed verdict (rare, and sticky for the interpolant)
+            # repeats the pipeline with the exact plan
+            if pending is not None and not AUTO_OPTIMISTIC_PIPELINE and not self._auto_verdict(*pending):
+                plan, f_eval, pending = exact_plan, f, None
+            out = self._interpolate_pipelined(torch, lambda: (plan, f_eval), x_new, f.shape[1], device,
+                                              after=entry)
+            if pending is not None and AUTO_OPTIMISTIC_PIPELINE and not self._auto_verdict(*pending):
+                out = self._interpolate_pipelined(torch, lambda: (exact_plan, f), x_new, f.shape[1],
+                                                  device)
             pending = None
-            out = self._interpolate_pipelined(torch, choose, x_new, f.shape[1], device, after=entry)
         else:
             if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):
                 x_new = x_new[:, :self.N]        # only the first N columns travel to the GPU
@@ -485,12 +496,17 @@ AUTO_MIN_POINTS = 8192      # smaller batches stay on the exact kernels
 AUTO_SAMPLE = 256           # rows of the first large batch evaluated by both kernels
 AUTO_TOL = 2.5e-13          # max |hier - exact| / max |exact| that enables the form
 AUTO_SIDE_STREAM = True     # the validation sample runs on a side stream, next to the batch kernel
+AUTO_OPTIMISTIC_PIPELINE = True   # host inputs: enqueue the chunks before the verdict is read
 
 
-# rows per host->device chunk of the pipelined path: a whole number of waves of the scalar
-# kernels (148 SMs x 3 blocks x 32 points x 8; also 12 waves of the 2-blocks-per-SM kernels),
-# measured best among 64k..340k rows on config 2 (tools/exp_e2e_numpy.py)
-_H2D_CHUNK = 113664
+# rows per host->device chunk of the pipelined path (tools/exp_e2e_ab.py, config 2 from pinned
+# memory): a first chunk of 113664 rows (a whole number of waves of the scalar kernels; nothing
+# overlaps its transfer) and steady chunks of twice that -- the transfer of a chunk (0.5 ms) then
+# hides under the evaluation of the previous one (0.9 ms) with half the per-chunk launches of the
+# 113664-row pipeline: 5.43 -> 5.18 ms per 10^6 points end to end; larger chunks lose (5.4-5.6 ms)
+_H2D_CHUNK = 227328
+_H2D_FIRST = 113664          # rows of the first chunk
+_H2D_MIN_ROWS = 4 * 113664    # smaller host batches are copied in one piece
 
 
 def _max_rel_deviation(torch, fast, exact):

@@ -32,10 +32,7 @@ def e2e():
 
 
 for rnd in range(2):
-    for side in (True, False):
-        for flags in ("0", "8"):
-            sgi.AUTO_SIDE_STREAM = side
-            os.environ["SGM_DEV_FLAGS"] = flags
-            it.hierarchical()._dev(0)[0].reload_knobs()
-            print(f"side stream {side}, dev flags {flags}: device step {timed(lambda: it.interpolate(x, f)):.3f} ms, "
-                  f"e2e step {timed(e2e):.3f} ms", flush=True)
+    for first, chunk in ((113664, 113664), (113664, 227328), (113664, 340992), (113664, 454656), (170496, 340992), (85248, 227328), (113664, 284160)):
+        sgi._H2D_FIRST, sgi._H2D_CHUNK = first, chunk
+        it._pipes = None                      # device / staging buffers are sized by the chunk
+        print(f"first chunk {first}, steady chunk {chunk}: e2e step {timed(e2e):.3f} ms", flush=True)
