@@ -284,7 +284,7 @@ class SGInterpolant:
                 if staging_free[b] is not None:
                     staging_free[b].synchronize()
                 src = buf[:hi - lo]
-                np.copyto(src.numpy(), x_host[lo:hi, :self.N], casting="same_kind")
+                _parallel_copy(src.numpy(), x_host[lo:hi, :self.N])
             else:
                 src = x_host[lo:hi, :self.N]
             xd = dev_buf[b][:hi - lo]
@@ -507,6 +507,29 @@ AUTO_OPTIMISTIC_PIPELINE = True   # host inputs: enqueue the chunks before the v
 _H2D_CHUNK = 227328
 _H2D_FIRST = 113664          # rows of the first chunk
 _H2D_MIN_ROWS = 4 * 113664    # smaller host batches are copied in one piece
+
+
+_STAGING_THREADS = 4
+_staging_pool = None
+
+
+def _parallel_copy(dst, src):
+    """dst[...] = src for the pageable -> pinned staging copy of the numpy path, row blocks on a
+    few threads (numpy releases the GIL inside the copy; one thread moves ~10 GB/s, which made the
+    staging copy the bottleneck of the numpy-in / numpy-out call)."""
+    global _staging_pool
+    rows = dst.shape[0]
+    if rows < 8192 or _STAGING_THREADS <= 1:
+        np.copyto(dst, src, casting="same_kind")
+        return
+    if _staging_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _staging_pool = ThreadPoolExecutor(max_workers=_STAGING_THREADS)
+    step = -(-rows // _STAGING_THREADS)
+    futs = [_staging_pool.submit(np.copyto, dst[a:a + step], src[a:a + step], "same_kind")
+            for a in range(0, rows, step)]
+    for fut in futs:
+        fut.result()
 
 
 def _max_rel_deviation(torch, fast, exact):
