@@ -230,13 +230,13 @@ class SGInterpolant:
                 device=device)
         return self._device_plans[device]
 
-    def _interpolate_pipelined(self, torch, choose, x_host, NF, device, after=None):
+    def _pipeline(self, torch, x_host, NF, device, after=None):
         """Host points (pinned torch tensor, or numpy array staged through two pinned
         buffers): the chunks are copied on a side stream while the previous chunk is being
-        evaluated; the kernels stay on the current stream, in order.  ``choose()`` returns the
-        (plan, values) pair to evaluate with; it is called after the first copy has been
-        enqueued, so the verdict of method="auto"'s validation (a host synchronisation on two
-        small launches) overlaps the first host-to-device transfer."""
+        evaluated; the kernels stay on the current stream, in order.  A generator in two phases:
+        ``next()`` enqueues the copy of the first chunk and returns -- the caller uploads the
+        nodal values, hierarchises and launches the validation sample meanwhile --, then
+        ``send((plan, values))`` runs the rest of the pipeline and returns the (P, NF) result."""
         P = x_host.shape[0]
         plan = f = None
         out = torch.empty((P, NF), dtype=torch.float64, device=device)
@@ -299,12 +299,17 @@ class SGInterpolant:
             # enqueue the evaluation of this chunk right away so that it overlaps the host
             # side staging copy of the next one
             if plan is None:
-                plan, f = choose()
+                plan, f = yield              # the first transfer is in flight
             compute.wait_event(done)
             plan.eval(xd, f, out[lo:hi])
             dev_free[b] = torch.cuda.Event()
             dev_free[b].record(compute)
-        return out
+        yield out
+
+    def _interpolate_pipelined(self, torch, plan, f, x_host, device, after=None):
+        pipe = self._pipeline(torch, x_host, f.shape[1], device, after)
+        next(pipe)
+        return pipe.send((plan, f))
 
     def _check_operator_constraints(self):
         if self._kind == _lib.KIND_CUBIC and self._fam_m.size and self._fam_m.min() < 4:
@@ -424,24 +429,31 @@ class SGInterpolant:
             device = torch.device("cuda", torch.cuda.current_device())
         n_used = int((self._num_nodes > 1).any(axis=0).nonzero()[0].max() + 1) \
             if (self._num_nodes > 1).any() else 0
-        f = _to_device(torch, f_on_SG, device)
-        if f.dim() != 2:
+        if not hasattr(f_on_SG, "shape"):
+            f_on_SG = np.asarray(f_on_SG, dtype=np.float64)
+        f_shape = tuple(f_on_SG.shape)
+        if len(f_shape) != 2:
             raise IndexError("f_on_SG must be 2-D (num_nodes, dim_f)")     # reference: tuple index out of range
-        if f.shape[0] < self.num_nodes:
-            raise IndexError(f"f_on_SG has {f.shape[0]} rows, the sparse grid {self.num_nodes}")
+        if f_shape[0] < self.num_nodes:
+            raise IndexError(f"f_on_SG has {f_shape[0]} rows, the sparse grid {self.num_nodes}")
         host_rows = x_new.shape[0] if hasattr(x_new, "shape") and len(x_new.shape) == 2 else 0
         if host_rows and x_new.shape[1] < n_used:
             raise IndexError(f"x_new has {x_new.shape[1]} columns, the interpolant uses {n_used}")
-        exact_plan = self.device_plan(device.index)
         pinned = as_torch and not x_new.is_cuda and x_new.is_pinned() and \
             x_new.dtype == torch.float64 and x_new.dim() == 2 and x_new.shape[1] >= self.N
         big_numpy = (not as_torch) and isinstance(x_new, np.ndarray) and x_new.ndim == 2 and \
             x_new.dtype == np.float64 and x_new.shape[1] >= self.N
         pipelined = (pinned or big_numpy) and host_rows >= _H2D_MIN_ROWS
-        entry = None
+        pipe = None
         if pipelined:
+            # host points: the transfer of the first chunk starts NOW, on the copy stream, and runs
+            # under the upload of the nodal values, the hierarchisation and the validation sample
             entry = torch.cuda.Event()
             entry.record(torch.cuda.current_stream(device))
+            pipe = self._pipeline(torch, x_new, f_shape[1], device, after=entry)
+            next(pipe)
+        f = _to_device(torch, f_on_SG, device)
+        exact_plan = self.device_plan(device.index)
         plan, f_eval, pending = exact_plan, f, None
         hp = self.hierarchical() if method == "hierarchical" else \
             (self._auto_candidate(host_rows) if method == "auto" else None)
@@ -456,11 +468,9 @@ class SGInterpolant:
             # repeats the pipeline with the exact plan
             if pending is not None and not AUTO_OPTIMISTIC_PIPELINE and not self._auto_verdict(*pending):
                 plan, f_eval, pending = exact_plan, f, None
-            out = self._interpolate_pipelined(torch, lambda: (plan, f_eval), x_new, f.shape[1], device,
-                                              after=entry)
+            out = pipe.send((plan, f_eval))
             if pending is not None and AUTO_OPTIMISTIC_PIPELINE and not self._auto_verdict(*pending):
-                out = self._interpolate_pipelined(torch, lambda: (exact_plan, f), x_new, f.shape[1],
-                                                  device)
+                out = self._interpolate_pipelined(torch, exact_plan, f, x_new, device)
             pending = None
         else:
             if not as_torch and host_rows and x_new.shape[1] > max(self.N, 1):

@@ -31,8 +31,5 @@ def e2e():
     oh.copy_(it.interpolate(xh, fh).reshape(P, 1), non_blocking=True)
 
 
-for rnd in range(2):
-    for first, chunk in ((113664, 113664), (113664, 227328), (113664, 340992), (113664, 454656), (170496, 340992), (85248, 227328), (113664, 284160)):
-        sgi._H2D_FIRST, sgi._H2D_CHUNK = first, chunk
-        it._pipes = None                      # device / staging buffers are sized by the chunk
-        print(f"first chunk {first}, steady chunk {chunk}: e2e step {timed(e2e):.3f} ms", flush=True)
+for rnd in range(3):
+    print(f"device step {timed(lambda: it.interpolate(x, f)):.3f} ms, e2e step {timed(e2e):.3f} ms", flush=True)
