@@ -220,3 +220,14 @@ def test_midset_replay_of_the_indicator_fixture_scripts(name):
             ms.enlarge_from_margin(arg) if op == "e" else ms.increase_dim()
         assert same(ms.mid_set, g[f"mid_{step}"])
         assert same(ms.reduced_margin, g[f"rm_{step}"])
+
+
+def test_parallel_staging_copy_equals_plain_copy():
+    """The pageable -> pinned staging copy of the numpy input path (row blocks on a few threads)."""
+    from sgmethods_b200 import sparse_grid_interpolant as sgi
+    rng = np.random.default_rng(5)
+    for rows, cols, used in ((100, 7, 7), (8192, 5, 3), (50001, 18, 16)):
+        src = rng.normal(size=(rows, cols))
+        dst = np.full((rows, used), np.nan)
+        sgi._parallel_copy(dst, src[:, :used])
+        assert np.array_equal(dst, src[:, :used])
