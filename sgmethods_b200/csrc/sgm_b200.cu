@@ -508,9 +508,14 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
                         double* out, int64_t ldo, double scale, int accumulate,
                         unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const SplitLaunch L = choose_split_launch<KIND>(plan, (P + 31) / 32 <= plan->sm_count);
-    const bool want_v1 = plan->knobs.force_kernel ? plan->knobs.force_kernel == 1
-                                                  : (plan->dev.T < 32 && P >= 16384);   // few terms, many points
-    if (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8)   // few terms / huge tables
+    // few terms, many points: one thread per point -- except for hierarchical plans whose value
+    // table was gathered in the grouped kernel's own layout (eval_one pregathers through h2_maps
+    // whenever the plan has group tables; found by tools/fuzz_auto.py: plans with < 32 tuples at
+    // >= 16384 points read that table with term offsets)
+    const bool h2_layout = KIND == SGM_HIER_PW_LINEAR && use_h2_kernel(plan);
+    const bool want_v1 = !h2_layout && (plan->knobs.force_kernel ? plan->knobs.force_kernel == 1
+                                                                 : (plan->dev.T < 32 && P >= 16384));
+    if (!h2_layout && (want_v1 || L.warps == 0 || L.blocks_per_sm * L.warps < 8))   // few terms / huge tables
         return launch_points<KIND>(plan, x, P, ldx, G, out, ldo, scale, accumulate, scratch,
                                    scratch_bytes, stream);
     const int64_t tiles = (P + 31) / 32;
@@ -554,6 +559,8 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
             SGM_CUDA(cudaGetLastError());
             return SGM_OK;
         }
+        // G is in the grouped kernel's layout: no other kernel may read it
+        return sgm_fail(SGM_ERR_OVERFLOW, "eval: the grouped hierarchical kernel does not fit this device");
     }
     if (KIND == SGM_HIER_PW_LINEAR && plan->all_packed && !plan->knobs.no_h1) {
         constexpr int HW = 16;
@@ -1502,7 +1509,12 @@ int sgm_plan_create(const sgm_plan_desc* desc, int device, sgm_plan** out) {
     d.h2_n_groups = (int)(h2_groups.size() / 12);
     d.h2_n_vals = (int)h2_maps.size();
     d.h2_root_off = h2_root;
-    plan->h2_ok = !h2_maps.empty();
+    {   // the grouped kernel must be launchable, because sgm_eval gathers the value table in its
+        // layout whenever h2_ok is set
+        const size_t h2_smem = (size_t)d.n_knots * 16 + (size_t)(d.B + 1) * 32 * 8 +
+                               (size_t)sgm::H2_LISTS * (32 * 8 + 4) + (size_t)(d.E + 1) * 32 * 2 + 64 + 64;
+        plan->h2_ok = !h2_maps.empty() && h2_smem <= (size_t)plan->max_smem_optin;
+    }
     d.seg_id = nullptr;
     d.seg_stride = 0;
     if (desc->n_seg > 0) {

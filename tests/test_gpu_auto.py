@@ -470,3 +470,27 @@ def test_max_rel_deviation_kernel_nan_rules():
                                                          torch.from_numpy(b2).cuda())))
     z = torch.zeros(5, dtype=torch.float64, device="cuda")
     assert float(sgi._max_rel_deviation(torch, z + 0.25, z)) == 0.25
+
+
+@pytest.mark.parametrize("kind", ["linear", "quadratic", "lagrange"])
+def test_few_tuple_plans_at_many_points(kind):
+    """Regression (found by tools/fuzz_auto.py): a hierarchical plan with fewer than 32 basis
+    tuples evaluated at >= 16384 points took the one-thread-per-point kernel while its value
+    table had been gathered in the grouped kernel's layout -- wrong values, silently."""
+    from sgmethods_b200 import tp_inteprolants as tpi
+    rng = np.random.default_rng(18)
+    S = mis.smolyak_mid_set(2, 3)                         # 10 multi-indices
+    if kind == "linear":
+        it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, L2K, verbose=False)
+        x = rng.normal(0, 1.2, (20000, 3))
+    else:
+        op = tpi.TPPwQuadraticInterpolator if kind == "quadratic" else tpi.TPLagrangeInterpolator
+        it = SGInterpolant(S, nodes_1d.cc_nodes, DBL, tp_interpolant=op, verbose=False)
+        x = rng.uniform(-1.0, 1.0, (20000, 3))
+    for NF in (1, 17):
+        f = rng.normal(size=(it.num_nodes, NF))
+        ref = sg_oracle.interpolate(oracle_plan_of(it), x[:64], f, kind=kind, squeeze=False)
+        exact = np.asarray(it.interpolate(x, f, method="combination")).reshape(-1, NF)
+        for method in ("auto", "hierarchical"):
+            got = np.asarray(it.interpolate(x, f, method=method)).reshape(-1, NF)
+            assert rel_dev(got[:64], ref) <= TOL and rel_dev(got, exact) <= TOL, (method, NF)
