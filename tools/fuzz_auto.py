@@ -24,8 +24,8 @@ while time.time() < t_end:
         knots, lev = nodes_1d.cc_nodes, (lambda q: np.where(q == 0, 1, 2 ** q + 1))
     it = SGInterpolant(S, knots, lev, tp_interpolant=op, verbose=False)
     P = int(rng.choice([1, 33, 4095, 8191, 8192, 8193, 20000, 470000]))
-    NF = int(rng.choice([1, 2, 17, 64, 129, 257, 300]))
-    if P * NF > 3e7:
+    NF = int(rng.choice([1, 2, 17, 64, 129, 257, 300, 512, 600, 1030]))
+    if P * NF > 4e7:
         NF = 1
     extra = int(rng.integers(0, 3))
     x = rng.normal(0, 1.2, (P, N + extra)) if kind == "linear" else rng.uniform(-1.1 if kind == "quadratic" else -1, 1, (P, N + extra))
@@ -54,3 +54,35 @@ while time.time() < t_end:
         print(f"CASE {seed0 + n} kind={kind} N={N} |S|={S.shape[0]} P={P} NF={NF} mode={mode}: {type(exc).__name__}: {exc}", flush=True)
     n += 1
 print(f"fuzz: {n} cases, {bad} failures", flush=True)
+
+# ---- multilevel interpolants: method='auto' / 'hierarchical' against 'combination'
+from sgmethods_b200 import multi_index_sets as mis  # noqa: E402
+from sgmethods_b200.multilevel_interpolant import MLInterpolant  # noqa: E402
+t_end = time.time() + budget / 4
+m = mbad = 0
+while time.time() < t_end:
+    rng = np.random.default_rng(90000 + seed0 + m)
+    kind = ("linear", "quadratic")[m % 2]
+    N, levels = int(rng.integers(1, 6)), int(rng.integers(2, 5))
+    op = tpi.TPPwLinearInterpolator if kind == "linear" else tpi.TPPwQuadraticInterpolator
+    lev = lambda q: np.where(q == 0, 1, 2 ** q + 1)  # noqa: E731
+    aniso = rng.uniform(1.0, 2.5, N)
+    seq = [SGInterpolant(mis.aniso_smolyak_mid_set(k + int(rng.integers(0, 2)) * 0, N, aniso), nodes_1d.cc_nodes, lev,
+                         tp_interpolant=op, verbose=False) for k in range(levels)]
+    NF = int(rng.choice([1, 3, 40, 260]))
+    P = int(rng.choice([500, 9000, 20000]))
+    ml = [rng.normal(size=(seq[levels - 1 - k].num_nodes, NF)) for k in range(levels)]
+    yy = rng.uniform(-1.1 if kind == "quadratic" else -1.3, 1.0, (P, N))
+    try:
+        mli = MLInterpolant(seq)
+        ref = np.asarray(mli.interpolate(yy, ml, method="combination"))
+        for method in ("auto", "hierarchical"):
+            got = np.asarray(mli.interpolate(yy, ml, method=method))
+            assert got.shape == ref.shape
+            dev = np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+            assert dev <= 1e-12, (method, dev)
+    except Exception as exc:  # noqa: BLE001
+        mbad += 1
+        print(f"ML CASE {m} kind={kind} N={N} levels={levels} P={P} NF={NF}: {type(exc).__name__}: {exc}", flush=True)
+    m += 1
+print(f"multilevel fuzz: {m} cases, {mbad} failures", flush=True)
