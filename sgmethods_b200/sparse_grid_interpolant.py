@@ -458,10 +458,19 @@ class SGInterpolant:
         hp = self.hierarchical() if method == "hierarchical" else \
             (self._auto_candidate(host_rows) if method == "auto" else None)
         if hp is not None:
-            plan = hp._dev(device.index)[0]
-            f_eval = hp.surpluses(f[:hp.M])      # nodal values -> hierarchical surpluses (GPU)
-            if method == "auto":
-                pending = self._auto_validation_launch(torch, hp, x_new, f, f_eval, device, host_rows)
+            try:
+                plan = hp._dev(device.index)[0]
+                f_eval = hp.surpluses(f[:hp.M])      # nodal values -> hierarchical surpluses (GPU)
+                if method == "auto":
+                    pending = self._auto_validation_launch(torch, hp, x_new, f, f_eval, device, host_rows)
+            except OverflowError as exc:
+                # tables of the work-reduced form do not fit the device's packed layouts / shared
+                # memory (very deep 1-D levels): "auto" keeps the exact kernels
+                if method != "auto":
+                    raise
+                self._auto_choice = "combination"
+                self.auto_validation = {"enabled": False, "reason": str(exc)}
+                hp, plan, f_eval, pending = None, exact_plan, f, None
         if pipelined:
             # optimistic: the chunks are enqueued with the fast plan while the validation sample
             # runs on its side stream; a failed verdict (rare, and sticky for the interpolant)

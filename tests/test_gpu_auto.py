@@ -494,3 +494,21 @@ def test_few_tuple_plans_at_many_points(kind):
         for method in ("auto", "hierarchical"):
             got = np.asarray(it.interpolate(x, f, method=method)).reshape(-1, NF)
             assert rel_dev(got[:64], ref) <= TOL and rel_dev(got, exact) <= TOL, (method, NF)
+
+
+def test_auto_keeps_exact_kernels_when_the_hierarchical_tables_do_not_fit():
+    """Very deep 1-D levels: the knot tables of the hierarchical plan (16 bytes per knot) exceed
+    shared memory while the exact plan (8 bytes per knot) still fits -- method='auto' must fall
+    back instead of failing; method='hierarchical' reports the limit."""
+    S = np.arange(13, dtype=int).reshape(-1, 1)           # levels 0..12: 16 382 knots in all
+    it = SGInterpolant(S, nodes_1d.unbounded_nodes_nested, L2K, verbose=False)
+    rng = np.random.default_rng(19)
+    f = rng.normal(size=(it.num_nodes, 1))
+    x = rng.normal(0, 1.5, (9000, 1))
+    exact = it.interpolate(x, f, method="combination")
+    assert np.array_equal(exact[:50], sg_oracle.interpolate(oracle_plan_of(it), x[:50], f))
+    auto = it.interpolate(x, f)
+    assert it.auto_validation["enabled"] is False and "reason" in it.auto_validation
+    assert np.array_equal(auto, exact)
+    with pytest.raises(OverflowError):
+        it.interpolate(x, f, method="hierarchical")
