@@ -254,15 +254,18 @@ class MLInterpolant:
                                         not isinstance(self._hier, Exception)):
             try:
                 hier = self._hier_surpluses(torch, fs, device)
-            except NotImplementedError as exc:
+            except (NotImplementedError, OverflowError) as exc:
                 if method == "hierarchical":
                     raise
                 self.auto_validation = {"enabled": False, "reason": str(exc)}
         if hier is not None and method == "auto":
             # validate THIS call: a sample of the batch through both forms, like SGInterpolant
             xs = x[::max(1, x.shape[0] // AUTO_SAMPLE)][:AUTO_SAMPLE].contiguous()
-            exact, fast = plan.eval(xs, F), hier[0].eval(xs, hier[1])
-            dev = float(_max_rel_deviation(torch, fast, exact))
+            exact = plan.eval(xs, F)
+            try:
+                dev = float(_max_rel_deviation(torch, hier[0].eval(xs, hier[1]), exact))
+            except OverflowError:            # tables of the work-reduced plan do not fit the device
+                dev = float("nan")
             ok = bool(np.isfinite(dev)) and dev <= AUTO_TOL
             self.auto_validation = {"enabled": ok, "max_rel_deviation": dev, "tolerance": AUTO_TOL,
                                     "sample_points": int(xs.shape[0])}
