@@ -529,26 +529,26 @@ _H2D_MIN_ROWS = 4 * 113664    # smaller host batches are copied in one piece
 
 
 _STAGING_THREADS = 4
-_staging_pool = None
 
 
 def _parallel_copy(dst, src):
     """dst[...] = src for the pageable -> pinned staging copy of the numpy path, row blocks on a
-    few threads (numpy releases the GIL inside the copy; one thread moves ~10 GB/s, which made the
-    staging copy the bottleneck of the numpy-in / numpy-out call)."""
-    global _staging_pool
+    few short-lived threads (numpy releases the GIL inside the copy; one thread moves ~10 GB/s,
+    which made the staging copy the bottleneck of the numpy-in / numpy-out call).  No persistent
+    pool: ``sample_on_SG(n_parallel > 1)`` forks, and forking a process with live threads is
+    discouraged."""
+    import threading
     rows = dst.shape[0]
     if rows < 8192 or _STAGING_THREADS <= 1:
         np.copyto(dst, src, casting="same_kind")
         return
-    if _staging_pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _staging_pool = ThreadPoolExecutor(max_workers=_STAGING_THREADS)
     step = -(-rows // _STAGING_THREADS)
-    futs = [_staging_pool.submit(np.copyto, dst[a:a + step], src[a:a + step], "same_kind")
-            for a in range(0, rows, step)]
-    for fut in futs:
-        fut.result()
+    threads = [threading.Thread(target=np.copyto, args=(dst[a:a + step], src[a:a + step], "same_kind"))
+               for a in range(0, rows, step)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
 
 
 def _max_rel_deviation(torch, fast, exact):

@@ -10,7 +10,6 @@ x = rng.normal(size=(P, it.N)); f = rng.normal(size=(it.num_nodes, 1))
 for rnd in range(2):
     for th in (1, 2, 4, 8):
         sgi._STAGING_THREADS = th
-        sgi._staging_pool = None
         it.interpolate(x, f); it.interpolate(x, f)
         ts = []
         for _ in range(7):
