@@ -987,3 +987,23 @@ def test_pipelined_numpy_path_equals_device_path():
     assert isinstance(got, np.ndarray) and np.array_equal(got, ref)
     got2 = it.interpolate(x[::-1].copy(), f)                          # staging buffers reused
     assert np.array_equal(got2, ref[::-1])
+
+
+def test_sharded_interpolant_over_nccl_on_two_gpus():
+    """ShardedInterpolant through NCCL + the CUDA kernels (tools/dist_check.py under torchrun):
+    points mode bit-identical to one GPU for the contract path and the exact path, terms mode
+    within 1e-12.  Needs two GPUs (skipped on a one-GPU box; the CPU suite covers the host logic
+    with gloo)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29577",
+                           os.path.join(root, "tools", "dist_check.py")],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert proc.stdout.count("root ok True") >= 6

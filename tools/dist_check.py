@@ -13,13 +13,16 @@ it = SGInterpolant(mis.smolyak_mid_set(4, 8), nodes_1d.unbounded_nodes_nested, l
 gen = torch.Generator(device="cpu").manual_seed(0)
 x = torch.randn((100003, 8), dtype=torch.float64, generator=gen).to(dev)
 f = torch.randn((it.num_nodes, 3), dtype=torch.float64, generator=gen).to(dev)
-single = it.device_plan(rank).eval(x, f)
-for mode in ("points", "terms"):
-    sh = ShardedInterpolant(it, mode=mode)
+single_exact = it.interpolate(x, f, method="combination").reshape(x.shape[0], -1)
+single_auto = it.interpolate(x, f).reshape(x.shape[0], -1)
+scale = float(single_exact.abs().max())
+for mode, method, single, bitwise in (("points", None, single_auto, True), ("points", "combination", single_exact, True),
+                                      ("terms", None, single_exact, False)):
+    sh = ShardedInterpolant(it, mode=mode, method=method)
     full = sh.interpolate(x, f, gather="all")
     root = sh.interpolate(x, f, gather="root")
-    err = float((full - single).abs().max() / single.abs().max())
-    ok_root = (root is None) if dist.get_rank() else bool(torch.allclose(root, single, rtol=0, atol=1e-12 * float(single.abs().max())))
-    print(f"rank {dist.get_rank()} mode {mode}: rel dev from single-GPU {err:.2e}, root ok {ok_root}", flush=True)
-    assert ok_root and (err == 0.0 if mode == "points" else err < 1e-12)
+    err = float((full - single).abs().max() / scale)
+    ok_root = (root is None) if dist.get_rank() else bool(torch.allclose(root, single, rtol=0, atol=1e-12 * scale))
+    print(f"rank {dist.get_rank()} mode {mode} method {method}: rel dev from single-GPU {err:.2e}, root ok {ok_root}", flush=True)
+    assert ok_root and (err == 0.0 if bitwise else err < 1e-12)
 dist.barrier(); dist.destroy_process_group()
