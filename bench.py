@@ -694,9 +694,10 @@ def main():
                        "step": "SGInterpolant.interpolate(x, f) on device-resident tensors, method='auto'",
                        "method_in_use": method, "auto_validation": getattr(it, "auto_validation", None),
                        "max_rel_deviation_from_exact_combination_formula": dev_rel},
-            # per step: hier_apply_all, validation (2 x pregather + eval), pregather, sort
-            # hist/scan/scatter, evaluation kernel -- or pregather, sort x3, eval on the exact path
-            "gpu_launches": (10 if hier else 5) * args.steps,
+            # per step: hier_apply_all, validation sample (2 x (pregather + eval) + deviation kernel),
+            # pregather + grouped kernel of the batch (no sort) -- or pregather, sort hist / scan /
+            # scatter, eval on the exact path
+            "gpu_launches": (8 if hier else 5) * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + f_host.numel() * 8),
                     "d2h_bytes_per_step": int(world * P * NF * 8), "steps": e2e_steps,

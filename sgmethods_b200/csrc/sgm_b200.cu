@@ -521,7 +521,16 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
     const int64_t tiles = (P + 31) / 32;
     int64_t blocks = std::min<int64_t>(tiles, (int64_t)plan->sm_count * L.blocks_per_sm);
     const int* perm = nullptr;
-    {
+    int* unsorted_counter = nullptr;     // grouped kernel: tile counter of an unsorted batch
+    // The grouped kernel does not sort: its value slots are size-aligned, so a gather touches one
+    // line whatever the lanes' brackets are, and the sort costs more than it saves (config 2
+    // 4.23 -> 4.08 ms, clustered points 5.54 -> 4.06 ms; tools/exp_nosort.py).  It still hands out
+    // its tiles from a global counter (dev switch 16 = sort anyway).
+    if (KIND == SGM_HIER_PW_LINEAR && use_h2_kernel(plan) && !(plan->knobs.dev_flags & 16) &&
+        P >= kSortMinPoints && scratch_bytes >= sort_scratch_bytes(P)) {
+        unsorted_counter = sort_tile_counter(scratch, P);
+        SGM_CUDA(cudaMemsetAsync(unsorted_counter, 0, 4, stream));
+    } else {
         int rc = locality_sort(plan, x, P, ldx, scratch, scratch_bytes, stream, &perm);
         if (rc) return rc;
     }
@@ -554,6 +563,7 @@ int launch_points_split(sgm_plan* plan, const double* x, int64_t P, int64_t ldx,
             PlanDev pd = plan->dev;
             pd.tile_counter = nullptr;
             if (perm && !(plan->knobs.dev_flags & 8)) pd.tile_counter = sort_tile_counter(scratch, P);   // zeroed by the sort
+            if (unsorted_counter) pd.tile_counter = unsorted_counter;
             sh.kern<<<(unsigned)blocks, sh.warps * 32, smem, stream>>>(pd, x, P, ldx, G, out, ldo,
                                                                      scale, accumulate, perm);
             SGM_CUDA(cudaGetLastError());

@@ -1441,11 +1441,16 @@ __global__ void sort_hist_kernel(const PlanDev pl, const double* __restrict__ x,
                                  int64_t ldx, unsigned* __restrict__ hist,
                                  unsigned short* __restrict__ keys, int* __restrict__ tile_counter) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;   // for the kernel that follows the sort
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned key = locality_key(pl, x + p * ldx);
-        keys[p] = (unsigned short)key;
-        atomicAdd(hist + key, 1u);
+    // warp-aggregated counting: lanes with the same key elect one lane that adds their number
+    // (clustered points fall into a handful of bins: one atomic per lane serialised on them)
+    for (int64_t p0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~(int64_t)31; p0 < P;
+         p0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p0 + (threadIdx.x & 31);
+        const bool act = p < P;
+        const unsigned key = act ? locality_key(pl, x + p * ldx) : 0xffffffffu;
+        if (act) keys[p] = (unsigned short)key;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (act && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + key, (unsigned)__popc(peers));
     }
 }
 // exclusive scan of the bins, two levels: every block scans 1024 consecutive bins in place
@@ -1488,10 +1493,18 @@ __global__ void sort_scatter_kernel(const unsigned short* __restrict__ keys, int
         for (int b = 0; b < n_blocks; ++b) { base[b] = run; run += block_total[b]; }
     }
     __syncthreads();
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned key = keys[p];
-        perm[base[key >> 10] + atomicAdd(offs + key, 1u)] = (int)p;
+    for (int64_t p0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~(int64_t)31; p0 < P;
+         p0 += (int64_t)gridDim.x * blockDim.x) {
+        const int lane = threadIdx.x & 31;
+        const int64_t p = p0 + lane;
+        const bool act = p < P;
+        const unsigned key = act ? keys[p] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        unsigned first = 0;
+        if (act && lane == leader) first = atomicAdd(offs + key, (unsigned)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (act) perm[base[key >> 10] + first + __popc(peers & ((1u << lane) - 1u))] = (int)p;
     }
 }
 
