@@ -352,11 +352,10 @@ class SGInterpolant:
         # runs on the others, instead of the batch waiting for two latency-bound small launches.
         main = torch.cuda.current_stream(device)
         sides = self.__dict__.setdefault("_auto_streams", {})
-        side = sides.get(device.index)
-        if side is None:
-            side = sides[device.index] = torch.cuda.Stream(device)
-        if not AUTO_SIDE_STREAM:
-            side = main
+        pair = sides.get(device.index)
+        if pair is None:
+            pair = sides[device.index] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        side, side2 = pair if AUTO_SIDE_STREAM else (main, main)
         ready = torch.cuda.Event()
         ready.record(main)                   # nodal values, surpluses and points are ready here
         side.wait_event(ready)
@@ -368,8 +367,19 @@ class SGInterpolant:
             xs = _to_device(torch, xs, device)
             if xs.shape[1] > self.N:
                 xs = xs[:, :self.N].contiguous()
-            fast = hp._dev(device.index)[0].eval(xs, alpha)
+            # the two sample evaluations start at once, each on its own stream (a kernel queued
+            # behind the other one would find every SM taken by the batch kernel and run last)
+            have_xs = torch.cuda.Event()
+            have_xs.record(side)
+            side2.wait_event(have_xs)
+            with torch.cuda.stream(side2):
+                fast = hp._dev(device.index)[0].eval(xs, alpha)
+                have_fast = torch.cuda.Event()
+                have_fast.record(side2)
             exact = self.device_plan(device.index).eval(xs, f)
+            side.wait_event(have_fast)
+            if side2 is not side:
+                fast.record_stream(side)         # allocated on side2, read by the comparison on side
             # NaN where the reference is NaN (Lagrange on a knot) counts as agreement; NaN in one
             # of the two makes the deviation NaN and fails the validation (sgm_max_rel_deviation)
             dev = _max_rel_deviation(torch, fast, exact)
@@ -427,8 +437,10 @@ class SGInterpolant:
             device = x_new.device if x_new.is_cuda else torch.device("cuda", torch.cuda.current_device())
         else:
             device = torch.device("cuda", torch.cuda.current_device())
-        n_used = int((self._num_nodes > 1).any(axis=0).nonzero()[0].max() + 1) \
-            if (self._num_nodes > 1).any() else 0
+        n_used = getattr(self, "_n_used", None)      # columns of x_new the interpolant reads
+        if n_used is None:                           # (a (T, N) reduction: once, not per call --
+            act = (self._num_nodes > 1).any(axis=0)  #  config 5: 10 ms of host time)
+            n_used = self._n_used = int(act.nonzero()[0].max() + 1) if act.any() else 0
         if not hasattr(f_on_SG, "shape"):
             f_on_SG = np.asarray(f_on_SG, dtype=np.float64)
         f_shape = tuple(f_on_SG.shape)
