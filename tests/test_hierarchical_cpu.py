@@ -312,3 +312,45 @@ def test_random_downward_closed_sets_all_operators(kind, seed):
     scale = np.max(np.abs(ref))
     assert np.max(np.abs(emulate(hp, x, f) - ref)) <= 1e-12 * scale
     assert np.max(np.abs(emulate_groups(hp, x, f) - ref)) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("kind", ["linear", "quadratic", "lagrange"])
+def test_coarse_operator_weights_are_the_one_dimensional_operator(kind):
+    """hierarchical._coarse_operator: sum_j w_j u(parent_j) is the level-(r-1) operator of the
+    oracle applied to u at a new knot of level r (also outside the coarse knots for pw-linear,
+    where the operator extrapolates from the end pair)."""
+    from sgmethods_b200 import _lib
+    from sgmethods_b200.hierarchical import _coarse_operator
+    rng = np.random.default_rng(23)
+    code = {"linear": _lib.KIND_LINEAR, "quadratic": _lib.KIND_QUADRATIC, "lagrange": _lib.KIND_LAGRANGE}[kind]
+    knots = nodes_1d.unbounded_nodes_nested if kind == "linear" else nodes_1d.cc_nodes
+    sizes = (3, 7, 15) if kind == "linear" else (3, 5, 9)
+    for m_c, m_f in zip(sizes[:-1], sizes[1:]):
+        gc, gf = np.asarray(knots(m_c), dtype=float), np.asarray(knots(m_f), dtype=float)
+        old = np.array([int(np.argmin(np.abs(gf - v))) for v in gc])
+        new = np.setdiff1d(np.arange(m_f), old)
+        par, wts = _coarse_operator(code, gf, old, new)
+        u = rng.normal(size=(m_f, 1))
+        mine = sum(w[:, None] * u[p] for p, w in zip(par, wts))
+        ref = sg_oracle.OPERATORS[kind]((gc,), u[old].reshape(m_c, 1), gf[new].reshape(-1, 1))
+        assert np.max(np.abs(mine - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_multilevel_hierarchical_form_rejects_what_it_cannot_represent():
+    from sgmethods_b200 import tp_inteprolants as tpi
+    from sgmethods_b200.multilevel_interpolant import MLInterpolant
+    dbl = lambda n: np.where(n == 0, 1, 2 ** n + 1)  # noqa: E731
+    lin = [SGInterpolant(mis.smolyak_mid_set(k, 2), nodes_1d.cc_nodes, dbl, verbose=False) for k in range(3)]
+    hps, moves = MLInterpolant(lin)._hierarchical()
+    assert sum(m[0].size for m in moves) == hps[-1].M          # every surplus comes from exactly one level
+    mixed = [lin[0], SGInterpolant(mis.smolyak_mid_set(1, 2), nodes_1d.cc_nodes, dbl,
+                                   tp_interpolant=tpi.TPPwQuadraticInterpolator, verbose=False)]
+    with pytest.raises(NotImplementedError):                   # levels with different operators
+        MLInterpolant(mixed)._hierarchical()
+    not_nested = [SGInterpolant(mis.smolyak_mid_set(2, 2), nodes_1d.cc_nodes, dbl, verbose=False),
+                  SGInterpolant(mis.tensor_product_mid_set(1, 2), nodes_1d.cc_nodes, dbl, verbose=False)]
+    with pytest.raises(NotImplementedError):                   # Lambda_0 is not a subset of Lambda_1
+        MLInterpolant(not_nested)._hierarchical()
+    other_knots = [lin[2], SGInterpolant(mis.smolyak_mid_set(3, 2), nodes_1d.equispaced_nodes, dbl, verbose=False)]
+    with pytest.raises(NotImplementedError):                   # the levels do not share their knots
+        MLInterpolant(other_knots)._hierarchical()
